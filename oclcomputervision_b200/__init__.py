@@ -1,0 +1,4 @@
+"""B200-native RAISR hot path of saturdaycoder/oclComputerVision."""
+from .raisr import ClRaisr, get_elapsed_ms  # noqa: F401
+
+__all__ = ["ClRaisr", "get_elapsed_ms"]

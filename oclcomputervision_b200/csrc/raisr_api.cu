@@ -1,0 +1,763 @@
+// raisr_api.cu -- C-ABI (include/raisr_b200.h) and host-side pipeline of the B200 RAISR path.
+//
+// Replaces the pyopencl plumbing of /root/reference/super_resolution/raisr.py:62-135 (context,
+// queue, per-call Image/Buffer creation, three enqueues, blocking wait) with persistent device
+// buffers, CUDA streams/events and two hand-written sm_100a kernels (raisr_prep.cuh,
+// raisr_filter.cuh).  No CPU fallback: every entry point that needs a device fails with
+// RAISR_E_CUDA when none is usable.
+#include "../../include/raisr_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "raisr_filter.cuh"
+#include "raisr_octet.cuh"
+#include "raisr_prep.cuh"
+
+using namespace raisr;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(e__ == cudaErrorMemoryAllocation ? RAISR_E_NOMEM : RAISR_E_CUDA,       \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__,     \
+                        __LINE__);                                                             \
+    } while (0)
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need)
+    {
+        if (need <= bytes) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e != cudaSuccess) return fail(RAISR_E_NOMEM, "cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
+        bytes = need;
+        return 0;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+struct ScaleTable {
+    DevBuf block;   // [type][bucket][132]  (filter_block_kernel)
+    DevBuf octet;   // [type][bucket][128]  (filter_octet_kernel, lane-major chunks)
+    bool set = false;
+};
+
+}  // namespace
+
+struct raisr_ctx {
+    int device = 0;
+    int n_angle = 24, n_strength = 3, n_coherence = 3;
+    int n_buckets = 216;
+    int sm_count = 0, clock_khz = 0;
+    char name[128] = {0};
+    float sq[kMaxQ], cq[kMaxQ];
+    cudaStream_t own_stream = nullptr, h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaStream_t user_stream = nullptr;
+    bool use_user_stream = false;
+    ScaleTable tables[5];  // index = scale (2..4)
+    DevBuf uext, hash, dsrc[2], ddst[2], dbg;
+    std::vector<cudaEvent_t> ev_pool;
+    long long launches = 0;
+    float last_prep_ms = 0, last_filter_ms = 0;
+    int filter_impl = 1;  // 0 = block (v1), 1 = octet
+    size_t chunk_budget = 96u << 20;
+
+    cudaStream_t stream() const { return use_user_stream ? user_stream : own_stream; }
+    cudaEvent_t ev(size_t i)
+    {
+        while (ev_pool.size() <= i) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ev_pool.push_back(e);
+        }
+        return ev_pool[i];
+    }
+};
+
+namespace {
+
+struct Guard {  // select the handle's device for the duration of a call
+    int prev = -1;
+    explicit Guard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~Guard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Geometry {
+    int sw, sh, dw, dh, s;
+    size_t uext_pitch;         // floats
+    size_t uext_frame;         // floats
+    size_t hash_pitch, hash_plane, hash_frame;  // bytes
+};
+
+Geometry make_geometry(int sw, int rows_out, int s)
+{
+    Geometry g;
+    g.sw = sw;
+    g.s = s;
+    g.dw = sw * s;
+    g.dh = rows_out;
+    g.sh = rows_out / s;
+    g.uext_pitch = round_up((size_t)g.dw + 2 * kMargin + 8, 4);
+    g.uext_frame = g.uext_pitch * (size_t)(rows_out + 2 * kMargin);
+    g.hash_pitch = round_up((size_t)sw + 16, 16);
+    g.hash_plane = g.hash_pitch * (size_t)g.sh;
+    g.hash_frame = g.hash_plane * (size_t)(s * s);
+    return g;
+}
+
+template <int S>
+void launch_prep_t(const PrepParams& p, cudaStream_t st, bool dbg)
+{
+    dim3 grid((p.dw + PT_W - 1) / PT_W, (p.rows + PT_H - 1) / PT_H, p.n_frames);
+    size_t smem = sizeof(PrepSmem);
+    if (dbg) {
+        cudaFuncSetAttribute(prep_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        prep_kernel<S, true><<<grid, PT_THREADS, smem, st>>>(p);
+    } else {
+        cudaFuncSetAttribute(prep_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        prep_kernel<S, false><<<grid, PT_THREADS, smem, st>>>(p);
+    }
+}
+
+int launch_prep(raisr_ctx* h, const PrepParams& p, int s, cudaStream_t st, bool dbg)
+{
+    switch (s) {
+    case 2: launch_prep_t<2>(p, st, dbg); break;
+    case 3: launch_prep_t<3>(p, st, dbg); break;
+    case 4: launch_prep_t<4>(p, st, dbg); break;
+    default: return fail(RAISR_E_UNSUPPORTED, "scale %d not supported (2, 3 or 4)", s);
+    }
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <int S, typename OutT>
+int launch_filter_block(raisr_ctx* h, FilterParams p, cudaStream_t st)
+{
+    constexpr int OTW = 64, OTH = 32, BR = 2, BC = 4;
+    using C = BlockCfg<S, OTW, OTH, BR, BC>;
+    p.tiles_x = (p.ow + OTW - 1) / OTW;
+    p.tiles_y = (p.oh + OTH - 1) / OTH;
+    size_t smem = ((size_t)p.n_buckets * kFStride + (size_t)C::TUH * C::TUW) * sizeof(float);
+    if (smem > 227 * 1024) return fail(RAISR_E_UNSUPPORTED, "filter table slice of %d buckets does not fit shared memory", p.n_buckets);
+    auto kern = filter_block_kernel<S, OTW, OTH, BR, BC, OutT>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int ntypes = S * S;
+    long long ntiles = (long long)p.tiles_x * p.tiles_y * p.n_frames;
+    int workers = (int)std::max<long long>(1, std::min<long long>(h->sm_count / ntypes, ntiles));
+    kern<<<workers * ntypes, C::NT, smem, st>>>(p);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <int S, typename OutT>
+int launch_filter_octet(raisr_ctx* h, FilterParams p, cudaStream_t st)
+{
+    using C = OctetCfg<S>;
+    p.tiles_x = (p.ow + C::OTW - 1) / C::OTW;
+    p.tiles_y = (p.oh + C::OTH - 1) / C::OTH;
+    size_t smem = octet_smem_bytes<S>(p.n_buckets);
+    if (smem > 227 * 1024) return fail(RAISR_E_UNSUPPORTED, "filter table slice of %d buckets does not fit shared memory", p.n_buckets);
+    auto kern = filter_octet_kernel<S, OutT>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int ntypes = S * S;
+    long long ntiles = (long long)p.tiles_x * p.tiles_y * p.n_frames;
+    int workers = (int)std::max<long long>(1, std::min<long long>(h->sm_count / ntypes, ntiles));
+    kern<<<workers * ntypes, C::NT, smem, st>>>(p);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <typename OutT>
+int launch_filter(raisr_ctx* h, FilterParams p, int s, cudaStream_t st)
+{
+    ScaleTable& t = h->tables[s];
+    if (h->filter_impl == 1) {
+        p.table = (const float*)t.octet.p;
+        switch (s) {
+        case 2: return launch_filter_octet<2, OutT>(h, p, st);
+        case 3: return launch_filter_octet<3, OutT>(h, p, st);
+        case 4: return launch_filter_octet<4, OutT>(h, p, st);
+        }
+    } else {
+        p.table = (const float*)t.block.p;
+        switch (s) {
+        case 2: return launch_filter_block<2, OutT>(h, p, st);
+        case 3: return launch_filter_block<3, OutT>(h, p, st);
+        case 4: return launch_filter_block<4, OutT>(h, p, st);
+        }
+    }
+    return fail(RAISR_E_UNSUPPORTED, "scale %d not supported", s);
+}
+
+int check_common(raisr_ctx* h, const void* src, int sw, int sh, size_t src_pitch, const void* dst, int dw,
+                 int dh, size_t dst_pitch, size_t dst_elem, int scale, int n_frames, bool need_table)
+{
+    if (!h) return fail(RAISR_E_ARG, "null handle");
+    if (!src || !dst) return fail(RAISR_E_ARG, "null image pointer");
+    if (scale < 2 || scale > 4) {
+        // the reference prints "Fatal. not trained for scale factor" and returns (raisr.py:90-94)
+        return fail(RAISR_E_UNSUPPORTED, "not trained for scale factor %d", scale);
+    }
+    if (need_table && !h->tables[scale].set)
+        return fail(RAISR_E_UNSUPPORTED, "not trained for scale factor %d (no filter table set)", scale);
+    if (sw < 1 || sh < 1 || n_frames < 1) return fail(RAISR_E_ARG, "bad source shape %dx%d x%d", sw, sh, n_frames);
+    if (dw != sw * scale || dh != sh * scale)
+        return fail(RAISR_E_ARG, "dst shape %dx%d is not %d x src shape %dx%d", dw, dh, scale, sw, sh);
+    if (src_pitch < (size_t)sw || dst_pitch < (size_t)dw * dst_elem) return fail(RAISR_E_ARG, "pitch smaller than a row");
+    if (dst_elem == 4 && (dst_pitch % 4)) return fail(RAISR_E_ARG, "float pitch must be a multiple of 4 bytes");
+    return 0;
+}
+
+// Enqueue prep+filter for `nf` frames that are already on the device.
+template <typename OutT>
+int enqueue_frames(raisr_ctx* h, const uint8_t* dsrc, int sw, int sh, size_t src_pitch, OutT* ddst,
+                   size_t dst_pitch, int scale, int nf, cudaStream_t st, bool timed, size_t ev_base)
+{
+    Geometry g = make_geometry(sw, sh * scale, scale);
+    size_t per_frame = g.uext_frame * sizeof(float);
+    int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nf, h->chunk_budget / std::max<size_t>(per_frame, 1)));
+    if (int rc = h->uext.ensure(per_frame * chunk)) return rc;
+    if (int rc = h->hash.ensure(g.hash_frame * chunk)) return rc;
+    for (int f0 = 0; f0 < nf; f0 += chunk) {
+        int n = std::min(chunk, nf - f0);
+        PrepParams pp{};
+        pp.src = dsrc + (size_t)f0 * src_pitch * sh;
+        pp.src_pitch = src_pitch;
+        pp.src_frame_stride = src_pitch * sh;
+        pp.sw = sw; pp.sh_glob = sh; pp.src_row0 = 0; pp.src_rows = sh;
+        pp.dw = g.dw; pp.dh_glob = g.dh; pp.y0 = 0; pp.rows = g.dh; pp.n_frames = n;
+        pp.uext = (float*)h->uext.p; pp.uext_pitch = g.uext_pitch; pp.uext_frame_stride = g.uext_frame;
+        pp.hash = (uint8_t*)h->hash.p; pp.hash_pitch = g.hash_pitch; pp.hash_plane_stride = g.hash_plane;
+        pp.hash_frame_stride = g.hash_frame;
+        pp.n_angle = h->n_angle; pp.n_strength = h->n_strength; pp.n_coherence = h->n_coherence;
+        memcpy(pp.sq, h->sq, sizeof(pp.sq)); memcpy(pp.cq, h->cq, sizeof(pp.cq));
+        FilterParams fp{};
+        fp.uext = pp.uext; fp.uext_pitch = g.uext_pitch; fp.uext_frame_stride = g.uext_frame;
+        fp.uext_rows = g.dh + 2 * kMargin;
+        fp.hash = pp.hash; fp.hash_pitch = g.hash_pitch; fp.hash_plane_stride = g.hash_plane;
+        fp.hash_frame_stride = g.hash_frame;
+        fp.n_buckets = h->n_buckets;
+        fp.dst = (unsigned char*)ddst + (size_t)f0 * dst_pitch * g.dh;
+        fp.dst_pitch = dst_pitch; fp.dst_frame_stride = dst_pitch * g.dh;
+        fp.ow = sw; fp.oh = sh; fp.n_frames = n;
+        size_t e = ev_base + 3 * (size_t)(f0 / chunk);
+        if (timed) cudaEventRecord(h->ev(e), st);
+        if (int rc = launch_prep(h, pp, scale, st, false)) return rc;
+        if (timed) cudaEventRecord(h->ev(e + 1), st);
+        if (int rc = launch_filter<OutT>(h, fp, scale, st)) return rc;
+        if (timed) cudaEventRecord(h->ev(e + 2), st);
+    }
+    return (nf + chunk - 1) / chunk;  // number of chunks (>0)
+}
+
+template <typename OutT>
+int upsample_impl(raisr_ctx* h, const uint8_t* src, int sw, int sh, size_t src_pitch, OutT* dst, int dw,
+                  int dh, size_t dst_pitch, int scale, int n_frames, int where, float ms[3])
+{
+    if (int rc = check_common(h, src, sw, sh, src_pitch, dst, dw, dh, dst_pitch, sizeof(OutT), scale, n_frames, true)) return rc;
+    Guard guard(h->device);
+    if (where == RAISR_DEVICE) {
+        cudaStream_t st = h->stream();
+        int nchunks = enqueue_frames<OutT>(h, src, sw, sh, src_pitch, dst, dst_pitch, scale, n_frames, st, ms != nullptr, 0);
+        if (nchunks < 0) return nchunks;
+        if (ms) {
+            CUDA_TRY(cudaStreamSynchronize(st));
+            float prep = 0, filt = 0;
+            for (int c = 0; c < nchunks; ++c) {
+                float a = 0, b = 0;
+                cudaEventElapsedTime(&a, h->ev(3 * c), h->ev(3 * c + 1));
+                cudaEventElapsedTime(&b, h->ev(3 * c + 1), h->ev(3 * c + 2));
+                prep += a; filt += b;
+            }
+            h->last_prep_ms = prep; h->last_filter_ms = filt;
+            ms[0] = 0; ms[1] = prep + filt; ms[2] = 0;
+        }
+        return 0;
+    }
+    if (where != RAISR_HOST) return fail(RAISR_E_ARG, "where must be RAISR_HOST or RAISR_DEVICE");
+
+    // Host path: chunks of frames flow H2D -> kernels -> D2H on three streams with double buffers.
+    const size_t src_frame = src_pitch * sh, dst_frame = dst_pitch * dh;
+    Geometry g = make_geometry(sw, dh, scale);
+    size_t per_frame = g.uext_frame * sizeof(float);
+    int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_frames, h->chunk_budget / std::max<size_t>(per_frame, 1)));
+    for (int b = 0; b < 2; ++b) {
+        if (int rc = h->dsrc[b].ensure(src_frame * chunk)) return rc;
+        if (int rc = h->ddst[b].ensure(dst_frame * chunk)) return rc;
+    }
+    cudaStream_t sc = h->own_stream, sh2d = h->h2d_stream, sd2h = h->d2h_stream;
+    const int nchunks = (n_frames + chunk - 1) / chunk;
+    // events: per chunk 9 = h2d start/stop, prep start/mid/stop (3), d2h start/stop, spare
+    auto E = [&](int c, int k) { return h->ev(16 + (size_t)c * 8 + k); };
+    for (int c = 0; c < nchunks; ++c) {
+        const int b = c & 1, f0 = c * chunk, n = std::min(chunk, n_frames - f0);
+        if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(sh2d, E(c - 2, 4), 0));  // kernels of chunk c-2 done with dsrc[b]
+        CUDA_TRY(cudaEventRecord(E(c, 0), sh2d));
+        CUDA_TRY(cudaMemcpyAsync(h->dsrc[b].p, src + (size_t)f0 * src_frame, src_frame * n, cudaMemcpyHostToDevice, sh2d));
+        CUDA_TRY(cudaEventRecord(E(c, 1), sh2d));
+        CUDA_TRY(cudaStreamWaitEvent(sc, E(c, 1), 0));
+        if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(sc, E(c - 2, 6), 0));    // D2H of chunk c-2 done with ddst[b]
+        // enqueue_frames records 3 events at ev_base.. : reuse slots 2,3,4 of this chunk
+        int rc = enqueue_frames<OutT>(h, (const uint8_t*)h->dsrc[b].p, sw, sh, src_pitch, (OutT*)h->ddst[b].p, dst_pitch,
+                                      scale, n, sc, true, 16 + (size_t)c * 8 + 2);
+        if (rc < 0) return rc;
+        CUDA_TRY(cudaStreamWaitEvent(sd2h, E(c, 4), 0));
+        CUDA_TRY(cudaEventRecord(E(c, 5), sd2h));
+        CUDA_TRY(cudaMemcpyAsync((unsigned char*)dst + (size_t)f0 * dst_frame, h->ddst[b].p, dst_frame * n, cudaMemcpyDeviceToHost, sd2h));
+        CUDA_TRY(cudaEventRecord(E(c, 6), sd2h));
+    }
+    CUDA_TRY(cudaStreamSynchronize(sd2h));
+    CUDA_TRY(cudaStreamSynchronize(sc));
+    CUDA_TRY(cudaStreamSynchronize(sh2d));
+    float t_h2d = 0, t_prep = 0, t_filt = 0, t_d2h = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        float a = 0;
+        cudaEventElapsedTime(&a, E(c, 0), E(c, 1)); t_h2d += a;
+        cudaEventElapsedTime(&a, E(c, 2), E(c, 3)); t_prep += a;
+        cudaEventElapsedTime(&a, E(c, 3), E(c, 4)); t_filt += a;
+        cudaEventElapsedTime(&a, E(c, 5), E(c, 6)); t_d2h += a;
+    }
+    h->last_prep_ms = t_prep; h->last_filter_ms = t_filt;
+    if (ms) { ms[0] = t_h2d; ms[1] = t_prep + t_filt; ms[2] = t_d2h; }
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters)
+{
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = threadIdx.x * 1e-3f + i;
+    float b = 1.0001f, c = 1e-4f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], b, c);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* raisr_last_error(void) { return g_err.c_str(); }
+const char* raisr_version(void) { return "raisr_b200 0.1 (sm_100a)"; }
+
+int raisr_create(raisr_t** out, int device, int n_angle, int n_strength, int n_coherence, int filter_len)
+{
+    if (!out) return fail(RAISR_E_ARG, "null out pointer");
+    *out = nullptr;
+    if (filter_len != kFlen) return fail(RAISR_E_ARG, "filter_len must be 11 (got %d)", filter_len);
+    if (n_angle < 1 || n_strength < 1 || n_coherence < 1 || n_strength - 1 > kMaxQ || n_coherence - 1 > kMaxQ)
+        return fail(RAISR_E_ARG, "bad bucket counts %d/%d/%d", n_angle, n_strength, n_coherence);
+    long long nb = (long long)n_angle * n_strength * n_coherence;
+    if (nb > 256) return fail(RAISR_E_ARG, "n_angle*n_strength*n_coherence = %lld exceeds 256 (one byte per pixel)", nb);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(RAISR_E_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count) return fail(RAISR_E_ARG, "device %d out of range (0..%d)", device, count - 1);
+    Guard guard(device);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(RAISR_E_CUDA, "device %d (%s, sm_%d%d) is not a Blackwell sm_100 part", device, prop.name, prop.major, prop.minor);
+    raisr_ctx* h = new raisr_ctx();
+    h->device = device;
+    h->n_angle = n_angle; h->n_strength = n_strength; h->n_coherence = n_coherence;
+    h->n_buckets = (int)nb;
+    h->sm_count = prop.multiProcessorCount;
+    cudaDeviceGetAttribute(&h->clock_khz, cudaDevAttrClockRate, device);
+    snprintf(h->name, sizeof(h->name), "%s", prop.name);
+    for (int i = 0; i < kMaxQ; ++i) { h->sq[i] = INFINITY; h->cq[i] = INFINITY; }
+    if (n_strength == 3) { h->sq[0] = 0.0001f; h->sq[1] = 0.001f; }   // raisr.py:112
+    if (n_coherence == 3) { h->cq[0] = 0.25f; h->cq[1] = 0.5f; }      // raisr.py:114
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return fail(RAISR_E_CUDA, "cudaStreamCreate failed");
+    }
+    const char* impl = getenv("RAISR_FILTER_IMPL");
+    if (impl && !strcmp(impl, "block")) h->filter_impl = 0;
+    *out = h;
+    return 0;
+}
+
+void raisr_destroy(raisr_t* h)
+{
+    if (!h) return;
+    Guard guard(h->device);
+    cudaDeviceSynchronize();
+    for (auto& t : h->tables) { t.block.release(); t.octet.release(); }
+    h->uext.release(); h->hash.release(); h->dbg.release();
+    for (int b = 0; b < 2; ++b) { h->dsrc[b].release(); h->ddst[b].release(); }
+    for (auto e : h->ev_pool) cudaEventDestroy(e);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+    delete h;
+}
+
+int raisr_set_filters(raisr_t* h, int scale, const float* table, size_t n_floats)
+{
+    if (!h || !table) return fail(RAISR_E_ARG, "null argument");
+    if (scale < 2 || scale > 4) return fail(RAISR_E_UNSUPPORTED, "scale %d not supported (2, 3 or 4)", scale);
+    const int ss = scale * scale, nb = h->n_buckets;
+    const size_t want = (size_t)nb * ss * kTaps;
+    if (n_floats != want) return fail(RAISR_E_ARG, "filter table has %zu floats, expected %zu = %d*%d*%d*%d*121", n_floats, want, h->n_angle, h->n_strength, h->n_coherence, ss);
+    Guard guard(h->device);
+    ScaleTable& t = h->tables[scale];
+    // block layout: [type][bucket][row i][12]; octet layout: see raisr_octet.cuh
+    std::vector<float> blk((size_t)ss * nb * kFStride, 0.0f), oct((size_t)ss * nb * kOctStride, 0.0f);
+    for (int type = 0; type < ss; ++type)
+        for (int b = 0; b < nb; ++b) {
+            const float* f = table + ((size_t)b * ss + type) * kTaps;   // raisr.cl:316-317 layout
+            float* d = &blk[((size_t)type * nb + b) * kFStride];
+            for (int i = 0; i < kFlen; ++i)
+                for (int j = 0; j < kFlen; ++j) d[i * kRowPad + j] = f[i * kFlen + j];
+            octet_pack_filter_s(f, &oct[((size_t)type * nb + b) * kOctStride], scale);
+        }
+    if (int rc = t.block.ensure(blk.size() * sizeof(float))) return rc;
+    if (int rc = t.octet.ensure(oct.size() * sizeof(float))) return rc;
+    CUDA_TRY(cudaMemcpy(t.block.p, blk.data(), blk.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(t.octet.p, oct.data(), oct.size() * sizeof(float), cudaMemcpyHostToDevice));
+    t.set = true;
+    return 0;
+}
+
+int raisr_set_quantizers(raisr_t* h, const float* strength_q, int n_sq, const float* coherence_q, int n_cq)
+{
+    if (!h || !strength_q || !coherence_q) return fail(RAISR_E_ARG, "null argument");
+    if (n_sq != h->n_strength - 1 || n_cq != h->n_coherence - 1)
+        return fail(RAISR_E_ARG, "expected %d strength and %d coherence thresholds", h->n_strength - 1, h->n_coherence - 1);
+    for (int i = 0; i < n_sq; ++i) h->sq[i] = strength_q[i];
+    for (int i = 0; i < n_cq; ++i) h->cq[i] = coherence_q[i];
+    return 0;
+}
+
+int raisr_set_stream(raisr_t* h, void* cuda_stream)
+{
+    if (!h) return fail(RAISR_E_ARG, "null handle");
+    h->user_stream = (cudaStream_t)cuda_stream;
+    h->use_user_stream = cuda_stream != nullptr;
+    return 0;
+}
+
+int raisr_set_option(raisr_t* h, const char* key, long long value)
+{
+    if (!h || !key) return fail(RAISR_E_ARG, "null argument");
+    if (!strcmp(key, "filter_impl")) { h->filter_impl = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "chunk_budget_bytes")) { h->chunk_budget = (size_t)std::max<long long>(value, 1 << 20); return 0; }
+    return fail(RAISR_E_ARG, "unknown option %s", key);
+}
+
+int raisr_upsample_u8(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_pitch, uint8_t* dst, int dw,
+                      int dh, size_t dst_pitch, int scale, int n_frames, int where, float ms[3])
+{
+    return upsample_impl<uint8_t>(h, src, sw, sh, src_pitch, dst, dw, dh, dst_pitch, scale, n_frames, where, ms);
+}
+
+int raisr_upsample_f32(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_pitch, float* dst, int dw,
+                       int dh, size_t dst_pitch, int scale, int n_frames, int where, float ms[3])
+{
+    return upsample_impl<float>(h, src, sw, sh, src_pitch, dst, dw, dh, dst_pitch, scale, n_frames, where, ms);
+}
+
+int raisr_bilinear_u8(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_pitch, uint8_t* dst, int dw,
+                      int dh, size_t dst_pitch, int scale, int n_frames, int where, float ms[3])
+{
+    if (!h) return fail(RAISR_E_ARG, "null handle");
+    if (!src || !dst) return fail(RAISR_E_ARG, "null image pointer");
+    if (scale < 1 || sw < 1 || sh < 1 || n_frames < 1 || dw != sw * scale || dh != sh * scale || dw < 2 || dh < 2)
+        return fail(RAISR_E_ARG, "bad shapes for bilinear: src %dx%d dst %dx%d scale %d", sw, sh, dw, dh, scale);
+    if (src_pitch < (size_t)sw || dst_pitch < (size_t)dw) return fail(RAISR_E_ARG, "pitch smaller than a row");
+    Guard guard(h->device);
+    cudaStream_t st = h->stream();
+    const size_t src_frame = src_pitch * sh, dst_frame = dst_pitch * dh;
+    const uint8_t* dsrc = src;
+    uint8_t* ddst = dst;
+    if (where == RAISR_HOST) {
+        if (int rc = h->dsrc[0].ensure(src_frame * n_frames)) return rc;
+        if (int rc = h->ddst[0].ensure(dst_frame * n_frames)) return rc;
+        dsrc = (const uint8_t*)h->dsrc[0].p; ddst = (uint8_t*)h->ddst[0].p;
+        cudaEventRecord(h->ev(0), st);
+        CUDA_TRY(cudaMemcpyAsync(h->dsrc[0].p, src, src_frame * n_frames, cudaMemcpyHostToDevice, st));
+    }
+    cudaEventRecord(h->ev(1), st);
+    BilinearParams bp{dsrc, src_pitch, src_frame, ddst, dst_pitch, dst_frame, sw, sh, dw, dh};
+    dim3 grid(((dw + 3) / 4 + 255) / 256, dh, n_frames);
+    bilinear_u8_kernel<<<grid, 256, 0, st>>>(bp);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    cudaEventRecord(h->ev(2), st);
+    if (where == RAISR_HOST) {
+        CUDA_TRY(cudaMemcpyAsync(dst, ddst, dst_frame * n_frames, cudaMemcpyDeviceToHost, st));
+        cudaEventRecord(h->ev(3), st);
+    }
+    if (where == RAISR_HOST || ms) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (ms) {
+            ms[0] = ms[2] = 0;
+            cudaEventElapsedTime(&ms[1], h->ev(1), h->ev(2));
+            if (where == RAISR_HOST) {
+                cudaEventElapsedTime(&ms[0], h->ev(0), h->ev(1));
+                cudaEventElapsedTime(&ms[2], h->ev(2), h->ev(3));
+            }
+        }
+    }
+    return 0;
+}
+
+int raisr_debug_hash(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_pitch, int scale, int32_t* hash,
+                     float* angle, float* l1, float* coherence, float* upscaled, int where)
+{
+    if (!h || !src) return fail(RAISR_E_ARG, "null argument");
+    if (scale < 2 || scale > 4) return fail(RAISR_E_UNSUPPORTED, "not trained for scale factor %d", scale);
+    if (sw < 1 || sh < 1 || src_pitch < (size_t)sw) return fail(RAISR_E_ARG, "bad source shape");
+    Guard guard(h->device);
+    cudaStream_t st = h->stream();
+    const int dw = sw * scale, dh = sh * scale;
+    Geometry g = make_geometry(sw, dh, scale);
+    if (int rc = h->uext.ensure(g.uext_frame * sizeof(float))) return rc;
+    if (int rc = h->hash.ensure(g.hash_frame)) return rc;
+    const size_t plane = (size_t)dw * dh;
+    const uint8_t* dsrc = src;
+    void* outs[5] = {hash, angle, l1, coherence, upscaled};
+    void* dev[5] = {hash, angle, l1, coherence, upscaled};
+    if (where == RAISR_HOST) {
+        if (int rc = h->dsrc[0].ensure(src_pitch * sh)) return rc;
+        if (int rc = h->dbg.ensure(plane * 4 * 5)) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h->dsrc[0].p, src, src_pitch * sh, cudaMemcpyHostToDevice, st));
+        dsrc = (const uint8_t*)h->dsrc[0].p;
+        for (int i = 0; i < 5; ++i) dev[i] = outs[i] ? (char*)h->dbg.p + plane * 4 * i : nullptr;
+    }
+    PrepParams pp{};
+    pp.src = dsrc; pp.src_pitch = src_pitch; pp.src_frame_stride = src_pitch * sh;
+    pp.sw = sw; pp.sh_glob = sh; pp.src_row0 = 0; pp.src_rows = sh;
+    pp.dw = dw; pp.dh_glob = dh; pp.y0 = 0; pp.rows = dh; pp.n_frames = 1;
+    pp.uext = (float*)h->uext.p; pp.uext_pitch = g.uext_pitch; pp.uext_frame_stride = g.uext_frame;
+    pp.hash = (uint8_t*)h->hash.p; pp.hash_pitch = g.hash_pitch; pp.hash_plane_stride = g.hash_plane;
+    pp.hash_frame_stride = g.hash_frame;
+    pp.n_angle = h->n_angle; pp.n_strength = h->n_strength; pp.n_coherence = h->n_coherence;
+    memcpy(pp.sq, h->sq, sizeof(pp.sq)); memcpy(pp.cq, h->cq, sizeof(pp.cq));
+    pp.dbg_hash = (int32_t*)dev[0]; pp.dbg_angle = (float*)dev[1]; pp.dbg_l1 = (float*)dev[2];
+    pp.dbg_coh = (float*)dev[3]; pp.dbg_u = (float*)dev[4]; pp.dbg_pitch = dw;
+    if (int rc = launch_prep(h, pp, scale, st, true)) return rc;
+    if (where == RAISR_HOST) {
+        for (int i = 0; i < 5; ++i)
+            if (outs[i]) CUDA_TRY(cudaMemcpyAsync(outs[i], dev[i], plane * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int raisr_band_src_rows(int global_sh, int scale, int dst_row0, int dst_rows, int* first, int* last)
+{
+    if (global_sh < 1 || scale < 1 || dst_rows < 1 || !first || !last) return fail(RAISR_E_ARG, "bad argument");
+    const int dh = global_sh * scale;
+    if (dh < 2) return fail(RAISR_E_ARG, "image too small");
+    auto map = [&](int y) {
+        volatile float a = (float)y / (float)(dh - 1);   // same op order as raisr.cl:209
+        volatile float b = a * (float)(global_sh - 1);
+        return (int)floorf(b);
+    };
+    int lo = map(dst_row0 - kMargin), hi = map(dst_row0 + dst_rows - 1 + kMargin) + 1;
+    *first = std::min(std::max(lo, 0), global_sh - 1);
+    *last = std::min(std::max(hi, 0), global_sh - 1);
+    return 0;
+}
+
+int raisr_upsample_band_u8(raisr_t* h, const uint8_t* src_rows_ptr, int sw, int global_sh, size_t src_pitch,
+                           int src_row0, int src_rows, uint8_t* dst, size_t dst_pitch, int dst_row0, int dst_rows,
+                           int scale)
+{
+    if (!h || !src_rows_ptr || !dst) return fail(RAISR_E_ARG, "null argument");
+    if (scale < 2 || scale > 4 || !h->tables[scale].set) return fail(RAISR_E_UNSUPPORTED, "not trained for scale factor %d", scale);
+    if (dst_row0 % scale || dst_rows % scale || dst_rows < scale) return fail(RAISR_E_ARG, "band rows must be multiples of the scale");
+    const int dw = sw * scale, dh = global_sh * scale;
+    if (dst_row0 < 0 || dst_row0 + dst_rows > dh) return fail(RAISR_E_ARG, "band outside the image");
+    int first, last;
+    if (int rc = raisr_band_src_rows(global_sh, scale, dst_row0, dst_rows, &first, &last)) return rc;
+    if (src_row0 > first || src_row0 + src_rows - 1 < last)
+        return fail(RAISR_E_ARG, "source window [%d,%d] does not cover rows [%d,%d] needed by the band", src_row0, src_row0 + src_rows - 1, first, last);
+    if (src_pitch < (size_t)sw || dst_pitch < (size_t)dw) return fail(RAISR_E_ARG, "pitch smaller than a row");
+    Guard guard(h->device);
+    cudaStream_t st = h->stream();
+    Geometry g = make_geometry(sw, dst_rows, scale);
+    if (int rc = h->uext.ensure(g.uext_frame * sizeof(float))) return rc;
+    if (int rc = h->hash.ensure(g.hash_frame)) return rc;
+    PrepParams pp{};
+    pp.src = src_rows_ptr; pp.src_pitch = src_pitch; pp.src_frame_stride = 0;
+    pp.sw = sw; pp.sh_glob = global_sh; pp.src_row0 = src_row0; pp.src_rows = src_rows;
+    pp.dw = dw; pp.dh_glob = dh; pp.y0 = dst_row0; pp.rows = dst_rows; pp.n_frames = 1;
+    pp.uext = (float*)h->uext.p; pp.uext_pitch = g.uext_pitch; pp.uext_frame_stride = g.uext_frame;
+    pp.hash = (uint8_t*)h->hash.p; pp.hash_pitch = g.hash_pitch; pp.hash_plane_stride = g.hash_plane;
+    pp.hash_frame_stride = g.hash_frame;
+    pp.n_angle = h->n_angle; pp.n_strength = h->n_strength; pp.n_coherence = h->n_coherence;
+    memcpy(pp.sq, h->sq, sizeof(pp.sq)); memcpy(pp.cq, h->cq, sizeof(pp.cq));
+    if (int rc = launch_prep(h, pp, scale, st, false)) return rc;
+    FilterParams fp{};
+    fp.uext = pp.uext; fp.uext_pitch = g.uext_pitch; fp.uext_frame_stride = g.uext_frame;
+    fp.uext_rows = dst_rows + 2 * kMargin;
+    fp.hash = pp.hash; fp.hash_pitch = g.hash_pitch; fp.hash_plane_stride = g.hash_plane; fp.hash_frame_stride = g.hash_frame;
+    fp.n_buckets = h->n_buckets;
+    fp.dst = dst; fp.dst_pitch = dst_pitch; fp.dst_frame_stride = 0;
+    fp.ow = sw; fp.oh = dst_rows / scale; fp.n_frames = 1;
+    return launch_filter<uint8_t>(h, fp, scale, st);
+}
+
+int raisr_ipc_export(const void* dev_ptr, unsigned char handle_out[64])
+{
+    if (!dev_ptr || !handle_out) return fail(RAISR_E_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t hd;
+    CUDA_TRY(cudaIpcGetMemHandle(&hd, const_cast<void*>(dev_ptr)));
+    memcpy(handle_out, &hd, 64);
+    return 0;
+}
+
+int raisr_ipc_open(const unsigned char handle_in[64], void** dev_ptr_out)
+{
+    if (!handle_in || !dev_ptr_out) return fail(RAISR_E_ARG, "null argument");
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle_in, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr_out, hd, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int raisr_ipc_close(void* dev_ptr)
+{
+    if (!dev_ptr) return fail(RAISR_E_ARG, "null argument");
+    CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+    return 0;
+}
+
+int raisr_p2p_copy2d(raisr_t* h, void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
+                     size_t rows)
+{
+    if (!h || !dst || !src) return fail(RAISR_E_ARG, "null argument");
+    Guard guard(h->device);
+    CUDA_TRY(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, cudaMemcpyDeviceToDevice, h->stream()));
+    return 0;
+}
+
+int raisr_host_alloc(void** p, size_t bytes)
+{
+    if (!p) return fail(RAISR_E_ARG, "null argument");
+    CUDA_TRY(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+    return 0;
+}
+
+int raisr_host_free(void* p)
+{
+    if (!p) return 0;
+    CUDA_TRY(cudaFreeHost(p));
+    return 0;
+}
+
+int raisr_sync(raisr_t* h)
+{
+    if (!h) return fail(RAISR_E_ARG, "null handle");
+    Guard guard(h->device);
+    CUDA_TRY(cudaStreamSynchronize(h->stream()));
+    CUDA_TRY(cudaStreamSynchronize(h->own_stream));
+    CUDA_TRY(cudaStreamSynchronize(h->h2d_stream));
+    CUDA_TRY(cudaStreamSynchronize(h->d2h_stream));
+    return 0;
+}
+
+long long raisr_launch_count(const raisr_t* h) { return h ? h->launches : 0; }
+
+int raisr_device_info(const raisr_t* h, int* sm_count, int* sm_clock_khz, char* name, int name_len)
+{
+    if (!h) return fail(RAISR_E_ARG, "null handle");
+    if (sm_count) *sm_count = h->sm_count;
+    if (sm_clock_khz) *sm_clock_khz = h->clock_khz;
+    if (name && name_len > 0) snprintf(name, name_len, "%s", h->name);
+    return 0;
+}
+
+int raisr_last_kernel_ms(const raisr_t* h, float* prep_ms, float* filter_ms)
+{
+    if (!h) return fail(RAISR_E_ARG, "null handle");
+    if (prep_ms) *prep_ms = h->last_prep_ms;
+    if (filter_ms) *filter_ms = h->last_filter_ms;
+    return 0;
+}
+
+int raisr_measure_ffma_tflops(raisr_t* h, float* tflops)
+{
+    if (!h || !tflops) return fail(RAISR_E_ARG, "null argument");
+    Guard guard(h->device);
+    cudaStream_t st = h->own_stream;
+    const int blocks = h->sm_count * 8, iters = 4000;
+    if (int rc = h->dbg.ensure((size_t)blocks * 256 * sizeof(float))) return rc;
+    ffma_peak_kernel<<<blocks, 256, 0, st>>>((float*)h->dbg.p, 200);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(h->ev(0), st);
+        ffma_peak_kernel<<<blocks, 256, 0, st>>>((float*)h->dbg.p, iters);
+        cudaEventRecord(h->ev(1), st);
+        CUDA_TRY(cudaStreamSynchronize(st));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->ev(0), h->ev(1));
+        best = std::min(best, ms);
+    }
+    h->launches += 6;
+    *tflops = (float)(2.0 * 128.0 * iters * (double)blocks * 256.0 / (best * 1e-3) / 1e12);
+    return 0;
+}
+
+}  // extern "C"
