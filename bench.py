@@ -1,0 +1,265 @@
+#!/usr/bin/env python
+"""bench.py -- RAISR 2x output Mpix/s on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch: BASELINE.json configs[1], 64 synthetic 1080p
+luma frames -> 4K (u8 in, u8 out) per GPU.  With N GPUs every rank processes its own 64 frames
+(frames are independent, no collective: weak scaling); `value` is the whole-job output Mpix/s.
+
+  value      device-resident throughput (inputs already in HBM), CUDA events, max over ranks
+  e2e        same metric through the C-ABI with HOST (pinned) buffers: H2D and D2H inside the call
+  roofline   FP32-FFMA roofline of SURVEY.md 8(d): 412 algorithmic FLOP per output pixel over the
+             summed kernel time of the step, against 2*128*SMs*max_clock and the measured FFMA peak
+  cpu_baseline  the oracle's C port (oracle/raisr_oracle.c) on the host cores of this box -- the
+             reference has no CPU RAISR path and its OpenCL path cannot run
+`--impl reference` times that CPU port alone (there is nothing else of the reference to time).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SW, SH, SCALE, FRAMES = 1920, 1080, 2, 64       # BASELINE.json configs[1]
+FLOP_PER_PX = 412.0                             # SURVEY.md 8(d), minimal form
+BYTES_PER_PX = 1.0 / (SCALE * SCALE) + 1.0      # u8 in -> u8 out
+
+
+def make_inputs(n_frames, rank):
+    from oclcomputervision_b200 import synth
+    pool = synth.synthetic_batch(8, SH, SW, pool=8, seed=1000 + 16 * rank)
+    reps = (n_frames + 7) // 8
+    return np.ascontiguousarray(np.tile(pool, (reps, 1, 1))[:n_frames])
+
+
+def cpu_baseline(budget_s=12.0):
+    """C oracle on all host threads, bounded sample of the bench workload."""
+    from oracle import raisr_oracle as O
+    from oclcomputervision_b200 import synth
+    F = synth.random_filters(SCALE)
+    frame = synth.synthetic_frame(SH, SW, 1000)
+    threads = min(len(os.sched_getaffinity(0)), O.c_max_threads())
+    t0 = time.perf_counter()
+    O.raisr_ref_c(frame, F, SCALE, nthreads=threads, want=("out_u8",))
+    one = time.perf_counter() - t0
+    n = int(max(1, min(16, budget_s / max(one, 1e-3))))
+    t0 = time.perf_counter()
+    for k in range(n):
+        O.raisr_ref_c(frame, F, SCALE, nthreads=threads, want=("out_u8",))
+    dt = time.perf_counter() - t0
+    mpix = n * SW * SH * SCALE * SCALE / dt / 1e6
+    return dict(value=round(mpix, 3), unit="Mpix/s", cores=threads, kind="port",
+                sample="%d frame(s) of the %dx%d->%dx%d workload, C oracle (fp32, OpenMP), %.1f s" %
+                       (n, SW, SH, SW * SCALE, SH * SCALE, dt))
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+        return dict(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)), samples=len(sm),
+                    power_w_max=float(max(pw)), reasons=sorted(reasons))
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cb = cpu_baseline(budget_s=max(4.0, 4.0 * args.steps))
+    line = dict(metric="RAISR 2x output Mpix/s", value=cb["value"], unit="Mpix/s", impl="reference",
+                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=None,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload="RAISR 2x 1080p->4K luma, random-init 24x3x3x4x121 table (BASELINE configs[1])",
+                            note="the reference has no CPU RAISR path and its OpenCL kernel cannot run here; "
+                                 "this is the oracle's C port of raisr.cl on the host cores"),
+                cpu_baseline=cb, gpu_launches=0,
+                e2e=dict(value=cb["value"], unit="Mpix/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=FRAMES, help="frames per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--filter-impl", type=int, default=None, help="1 octet (default), 0 block")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the RAISR path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from oclcomputervision_b200 import ClRaisr, synth, _cabi
+    import ctypes
+    F = synth.random_filters(SCALE)
+    r = ClRaisr(1, filters=F, device=local_rank)
+    if args.filter_impl is not None:
+        r.set_option("filter_impl", args.filter_impl)
+    info = r.device_info()
+    n = args.frames
+    dw, dh = SW * SCALE, SH * SCALE
+    host_src = make_inputs(n, rank)
+    src = torch.from_numpy(host_src).cuda()
+    dst = torch.empty((n, dh, dw), dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+    r.set_stream(stream.cuda_stream)
+    px_per_step = n * dw * dh
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(timed):
+        return r.upsample_device(src.data_ptr(), SW, SH, SW, dst.data_ptr(), dw, SCALE, n, np.uint8, timed=timed)
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    barrier()
+    launches0 = r.launch_count()
+    sampler = ClockSampler(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prep_ms = filt_ms = 0.0
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step(True)                       # per-kernel CUDA events on the launch stream, inside the region
+        a, b = r.last_kernel_ms()
+        prep_ms += a; filt_ms += b
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = r.launch_count() - launches0
+    elapsed_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = world * px_per_step * args.steps / (elapsed_ms * 1e-3) / 1e6
+
+    # ---- end to end through the C-ABI with pinned host buffers (H2D + kernels + D2H per step)
+    lib = _cabi.load()
+    hp_src, hp_dst = ctypes.c_void_p(), ctypes.c_void_p()
+    _cabi.check(lib.raisr_host_alloc(ctypes.byref(hp_src), n * SW * SH))
+    _cabi.check(lib.raisr_host_alloc(ctypes.byref(hp_dst), n * dw * dh))
+    ctypes.memmove(hp_src.value, host_src.ctypes.data, n * SW * SH)
+    r.set_stream(0)
+    ms3 = (ctypes.c_float * 3)()
+
+    def e2e_step():
+        _cabi.check(lib.raisr_upsample_u8(r._h, hp_src.value, SW, SH, SW, hp_dst.value, dw, dh, dw, SCALE, n,
+                                          _cabi.RAISR_HOST, ms3))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * px_per_step * e2e_steps / float(te.item()) / 1e6
+    out_host = np.ctypeslib.as_array((ctypes.c_ubyte * (dw * dh)).from_address(hp_dst.value)).reshape(dh, dw)
+    same_as_device = bool(np.array_equal(out_host, dst[0].cpu().numpy()))
+    e2e_ms3 = [float(x) for x in ms3]
+    lib.raisr_host_free(hp_src); lib.raisr_host_free(hp_dst)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        ffma_meas = r.measure_ffma_tflops()
+        peak_nominal = 2.0 * 128 * info["sm_count"] * info["sm_clock_khz"] * 1e3 / 1e12
+        kern_s = (prep_ms + filt_ms) * 1e-3
+        achieved_tf = FLOP_PER_PX * px_per_step * args.steps / kern_s / 1e12
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        roofline = dict(bound="fp32_ffma", achieved=round(achieved_tf, 3), peak=round(peak_nominal, 2), unit="TFLOP/s",
+                        frac=round(achieved_tf / peak_nominal, 4), traffic=None,
+                        peak_source="2*128*SMs*clocks.max.sm (SURVEY 8(d)); measured register-only FFMA kernel: %.1f TFLOP/s" % ffma_meas,
+                        frac_of_measured_ffma=round(achieved_tf / ffma_meas, 4),
+                        flop_per_px=FLOP_PER_PX,
+                        kernels=dict(prep_ms_per_step=round(prep_ms / args.steps, 3), filter_ms_per_step=round(filt_ms / args.steps, 3),
+                                     filter_share=round(filt_ms / (prep_ms + filt_ms), 3)),
+                        hbm=dict(algorithmic_bytes_per_px=BYTES_PER_PX,
+                                 achieved_gbs=round(BYTES_PER_PX * px_per_step * args.steps / kern_s / 1e9, 1),
+                                 peak_gbs=hbm_peak, peak_source="MEASURED_PEAKS.json" if peaks else "fallback 6650"))
+        cb = None if args.no_cpu_baseline else cpu_baseline()
+        line = dict(metric="RAISR 2x output Mpix/s", value=round(value, 1), unit="Mpix/s", n_gpus=world, steps=args.steps,
+                    warmup=max(args.warmup, 3), ms_per_step=round(elapsed_ms / args.steps, 3), higher_is_better=True,
+                    scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload="RAISR 2x 1080p->4K luma u8->u8, batch of %d synthetic frames per GPU, "
+                                         "random-init 24x3x3x4x121 fp32 table (BASELINE configs[1])" % n,
+                                frames_per_gpu=n, src="%dx%d" % (SW, SH), dst="%dx%d" % (dw, dh), parallelism="frames sharded, no collective",
+                                l2="per-step working set (%.0f MB in + %.0f MB out) exceeds the 126 MB L2" % (n * SW * SH / 1e6, n * dw * dh / 1e6),
+                                device=info["name"]),
+                    clocks=clocks, gpu_launches=int(launches),
+                    e2e=dict(value=round(e2e_value, 1), unit="Mpix/s", h2d_bytes_per_step=n * SW * SH, d2h_bytes_per_step=n * dw * dh,
+                             h2d_kernel_d2h_ms=[round(x, 3) for x in e2e_ms3], matches_device_path=same_as_device,
+                             api="raisr_upsample_u8(where=RAISR_HOST), pinned buffers"),
+                    roofline=roofline, cpu_baseline=cb)
+        print(json.dumps(line), flush=True)
+    r.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -178,7 +178,7 @@ int launch_prep(raisr_ctx* h, const PrepParams& p, int s, cudaStream_t st, bool 
 template <int S, typename OutT>
 int launch_filter_block(raisr_ctx* h, FilterParams p, cudaStream_t st)
 {
-    constexpr int OTW = 64, OTH = 32, BR = 2, BC = 4;
+    constexpr int OTW = S == 4 ? 32 : 64, OTH = S == 4 ? 16 : 32, BR = 2, BC = 4;
     using C = BlockCfg<S, OTW, OTH, BR, BC>;
     p.tiles_x = (p.ow + OTW - 1) / OTW;
     p.tiles_y = (p.oh + OTH - 1) / OTH;
