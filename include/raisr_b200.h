@@ -129,6 +129,11 @@ int raisr_ipc_close(void* dev_ptr);
 int raisr_p2p_copy2d(raisr_t* h, void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
                      size_t width_bytes, size_t rows);
 
+/* Plain device allocations on the handle's device (cudaMalloc, so they can be exported with
+ * raisr_ipc_export; framework caching allocators hand out sub-blocks that cannot). */
+int raisr_dev_alloc(raisr_t* h, void** p, size_t bytes);
+int raisr_dev_free(raisr_t* h, void* p);
+
 /* Pinned host memory for the HOST path (stands in for mem_flags.USE_HOST_PTR, raisr.py:99-115). */
 int raisr_host_alloc(void** p, size_t bytes);
 int raisr_host_free(void* p);

@@ -39,6 +39,8 @@ SIGNATURES = {
     "raisr_ipc_open": (c_int, [POINTER(c_ubyte), POINTER(c_void_p)]),
     "raisr_ipc_close": (c_int, [c_void_p]),
     "raisr_p2p_copy2d": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t]),
+    "raisr_dev_alloc": (c_int, [c_void_p, POINTER(c_void_p), c_size_t]),
+    "raisr_dev_free": (c_int, [c_void_p, c_void_p]),
     "raisr_host_alloc": (c_int, [POINTER(c_void_p), c_size_t]),
     "raisr_host_free": (c_int, [c_void_p]),
     "raisr_sync": (c_int, [c_void_p]),

@@ -148,18 +148,21 @@ Geometry make_geometry(int sw, int rows_out, int s)
     return g;
 }
 
-template <int S>
-void launch_prep_t(const PrepParams& p, cudaStream_t st, bool dbg)
+template <int S, bool DBG, int NQ>
+void launch_prep_q(const PrepParams& p, cudaStream_t st)
 {
     dim3 grid((p.dw + PT_W - 1) / PT_W, (p.rows + PT_H - 1) / PT_H, p.n_frames);
     size_t smem = sizeof(PrepSmem);
-    if (dbg) {
-        cudaFuncSetAttribute(prep_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        prep_kernel<S, true><<<grid, PT_THREADS, smem, st>>>(p);
-    } else {
-        cudaFuncSetAttribute(prep_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        prep_kernel<S, false><<<grid, PT_THREADS, smem, st>>>(p);
-    }
+    cudaFuncSetAttribute(prep_kernel<S, DBG, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    prep_kernel<S, DBG, NQ><<<grid, PT_THREADS, smem, st>>>(p);
+}
+
+template <int S>
+void launch_prep_t(const PrepParams& p, cudaStream_t st, bool dbg)
+{
+    const bool small = p.n_strength <= 3 && p.n_coherence <= 3;   // the reference's 3 x 3 (raisr.cl:9-15)
+    if (dbg) small ? launch_prep_q<S, true, 2>(p, st) : launch_prep_q<S, true, kMaxQ>(p, st);
+    else small ? launch_prep_q<S, false, 2>(p, st) : launch_prep_q<S, false, kMaxQ>(p, st);
 }
 
 int launch_prep(raisr_ctx* h, const PrepParams& p, int s, cudaStream_t st, bool dbg)
@@ -420,7 +423,7 @@ int raisr_create(raisr_t** out, int device, int n_angle, int n_strength, int n_c
     h->sm_count = prop.multiProcessorCount;
     cudaDeviceGetAttribute(&h->clock_khz, cudaDevAttrClockRate, device);
     snprintf(h->name, sizeof(h->name), "%s", prop.name);
-    for (int i = 0; i < kMaxQ; ++i) { h->sq[i] = INFINITY; h->cq[i] = INFINITY; }
+    for (int i = 0; i < kMaxQ; ++i) { h->sq[i] = -INFINITY; h->cq[i] = -INFINITY; }
     if (n_strength == 3) { h->sq[0] = 0.0001f; h->sq[1] = 0.001f; }   // raisr.py:112
     if (n_coherence == 3) { h->cq[0] = 0.25f; h->cq[1] = 0.5f; }      // raisr.py:114
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -690,6 +693,23 @@ int raisr_p2p_copy2d(raisr_t* h, void* dst, size_t dst_pitch, const void* src, s
     if (!h || !dst || !src) return fail(RAISR_E_ARG, "null argument");
     Guard guard(h->device);
     CUDA_TRY(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, cudaMemcpyDeviceToDevice, h->stream()));
+    return 0;
+}
+
+int raisr_dev_alloc(raisr_t* h, void** p, size_t bytes)
+{
+    if (!h || !p) return fail(RAISR_E_ARG, "null argument");
+    Guard guard(h->device);
+    CUDA_TRY(cudaMalloc(p, bytes));
+    return 0;
+}
+
+int raisr_dev_free(raisr_t* h, void* p)
+{
+    if (!h) return fail(RAISR_E_ARG, "null handle");
+    if (!p) return 0;
+    Guard guard(h->device);
+    CUDA_TRY(cudaFree(p));
     return 0;
 }
 
