@@ -47,7 +47,7 @@ def cpu_baseline(budget_s=12.0):
     from oclcomputervision_b200 import synth
     F = synth.random_filters(SCALE)
     frame = synth.synthetic_frame(SH, SW, 1000)
-    threads = min(len(os.sched_getaffinity(0)), O.c_max_threads())
+    threads = len(os.sched_getaffinity(0))   # torchrun exports OMP_NUM_THREADS=1; the oracle sets its own count
     t0 = time.perf_counter()
     O.raisr_ref_c(frame, F, SCALE, nthreads=threads, want=("out_u8",))
     one = time.perf_counter() - t0
@@ -241,7 +241,7 @@ def main():
                         hbm=dict(algorithmic_bytes_per_px=BYTES_PER_PX,
                                  achieved_gbs=round(BYTES_PER_PX * px_per_step * args.steps / kern_s / 1e9, 1),
                                  peak_gbs=hbm_peak, peak_source="MEASURED_PEAKS.json" if peaks else "fallback 6650"))
-        cb = None if args.no_cpu_baseline else cpu_baseline()
+        cb = None if (args.no_cpu_baseline or world > 1) else cpu_baseline()
         line = dict(metric="RAISR 2x output Mpix/s", value=round(value, 1), unit="Mpix/s", n_gpus=world, steps=args.steps,
                     warmup=max(args.warmup, 3), ms_per_step=round(elapsed_ms / args.steps, 3), higher_is_better=True,
                     scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
