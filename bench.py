@@ -127,6 +127,7 @@ def main():
     ap.add_argument("--frames", type=int, default=FRAMES, help="frames per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--filter-impl", type=int, default=None, help="1 octet (default), 0 block")
+    ap.add_argument("--dbg-flags", type=int, default=0, help="kernel timing experiments (results invalid)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -149,6 +150,8 @@ def main():
     r = ClRaisr(1, filters=F, device=local_rank)
     if args.filter_impl is not None:
         r.set_option("filter_impl", args.filter_impl)
+    if args.dbg_flags:
+        r.set_option("dbg_flags", args.dbg_flags)
     info = r.device_info()
     n = args.frames
     dw, dh = SW * SCALE, SH * SCALE

@@ -35,6 +35,7 @@ struct FilterParams {
     int ow, oh;               // own columns (= source width) / own rows of this launch (= rows / S)
     int n_frames;
     int tiles_x, tiles_y;
+    int dbg_flags;            // timing experiments only (results become wrong when non-zero)
 };
 
 template <int S, int OTW, int OTH, int BR, int BC>

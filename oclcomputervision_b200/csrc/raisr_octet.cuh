@@ -56,61 +56,95 @@ inline void octet_pack_filter_s(const float* f, float* rec, int S)
 
 template <int S>
 struct OctetCfg;
-// OTW x OTH own pixels per tile, items of IW pixels (one octet each), NT threads, TUW = odd row
-// pitch of the U tile in floats chosen so the per-pixel LDS.32 of a warp (4 octets on consecutive
-// own rows) are bank-conflict-free for the 11-runs and nearly so for the 5-runs.
+// OTW x OTH own pixels per tile, one item of IW pixels per octet, NT threads.
 template <>
-struct OctetCfg<2> { static constexpr int OTW = 64, OTH = 32, IW = 32, NT = 512, TUW = 153; };
+struct OctetCfg<2> { static constexpr int OTW = 64, OTH = 32, IW = 32, NT = 512; };
 template <>
-struct OctetCfg<3> { static constexpr int OTW = 64, OTH = 16, IW = 16, NT = 512, TUW = 203; };
+struct OctetCfg<3> { static constexpr int OTW = 64, OTH = 16, IW = 16, NT = 512; };
 template <>
-struct OctetCfg<4> { static constexpr int OTW = 32, OTH = 16, IW = 16, NT = 256, TUW = 149; };
+struct OctetCfg<4> { static constexpr int OTW = 32, OTH = 16, IW = 16, NT = 256; };
 
 template <int S>
 struct OctetGeom {
     using C = OctetCfg<S>;
-    static constexpr int TUH = S * (C::OTH - 1) + kFlen;     // tile rows
-    static constexpr int NCOLS = S * (C::OTW - 1) + kFlen;   // tile columns actually used
-    static constexpr int TUW = C::TUW;
+    static constexpr int TUH = S * (C::OTH - 1) + kFlen;                              // tile rows
+    static constexpr int TUW = ((S * (C::OTW - 1) + kFlen + (S - 1)) + 3) / 4 * 4;      // tile pitch, 16-byte rows
     static constexpr int NEWF = S;                 // fresh values per pixel in the 11-run
     static constexpr int NEWP = S < 5 ? S : 5;     // fresh values per pixel in the 5-run
+    static constexpr int WF = (S == 3) ? 12 : 16;  // circular register window of the 11-run: 8*S % WF == 0
+    static constexpr int WP = 8;                   // circular register window of the 5-run:  8*S % 8 == 0
     static constexpr int SEGS = C::OTW / C::IW;
     static constexpr int ITEMS = C::OTH * SEGS;
     static constexpr int NOCT = C::NT / 8;
-    static constexpr int TILE_FLOATS = (TUH * TUW + 3) / 4 * 4;
-    static_assert(C::IW % 16 == 0 && C::OTW % C::IW == 0, "items are whole batches of 8 pixels, hashes come 16 at a time");
-    static_assert(TUW >= NCOLS && (TUW & 1), "odd pitch that holds a tile row");
+    static constexpr int TILE_FLOATS = TUH * TUW;
+    static constexpr int HASH_BYTES = C::OTH * C::OTW;   // one byte per own pixel of the tile
+    static constexpr int BUF_BYTES = TILE_FLOATS * 4 + HASH_BYTES;
+    static_assert(C::IW % 8 == 0 && C::OTW % C::IW == 0 && C::OTW % 16 == 0, "items are whole batches of 8 pixels");
+    static_assert((8 * S) % WF == 0 && WF >= kFlen && BUF_BYTES % 16 == 0, "window period / alignment");
+    static_assert(ITEMS == NOCT, "one item per octet and tile");
 };
 
 template <int S>
 inline size_t octet_smem_bytes(int n_buckets)
 {
     using G = OctetGeom<S>;
-    return ((size_t)n_buckets * kOctStride + 2 * (size_t)G::TILE_FLOATS) * sizeof(float);
+    size_t table = (size_t)(n_buckets > 256 ? n_buckets : 256) * kOctStride * sizeof(float);  // any hash byte stays inside
+    return table + 2 * (size_t)G::BUF_BYTES;
 }
 
-__device__ __forceinline__ void cp_async4(unsigned smem_addr, const float* gptr)
+__device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gptr)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gptr) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Asynchronous fill of one U tile: rows er0.., columns ec0.. of the extended upscaled frame.
+// Position of the persistent worker in the (frame, tile row, tile column) sequence, advanced by
+// `nworkers` tiles at a time without integer divisions.
+struct TileCursor {
+    int frame, ty, tx;
+    __device__ __forceinline__ void init(int tile, int tiles_x, int tiles_y)
+    {
+        const int per_frame = tiles_x * tiles_y;
+        frame = tile / per_frame;
+        const int rem = tile - frame * per_frame;
+        ty = rem / tiles_x;
+        tx = rem - ty * tiles_x;
+    }
+    __device__ __forceinline__ void advance(int n, int tiles_x, int tiles_y)
+    {
+        tx += n;
+        while (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+        while (ty >= tiles_y) { ty -= tiles_y; ++frame; }
+    }
+};
+
+// Asynchronous fill of one tile buffer: the U tile (rows er0.., columns ec0.. of the extended
+// upscaled frame, ec0 a multiple of 4) followed by the tile's hash bytes (OTH rows of OTW bytes).
 template <int S>
-__device__ __forceinline__ void octet_issue_tile(const FilterParams& p, float* buf, int frame, int er0, int ec0)
+__device__ __forceinline__ void octet_issue_tile(const FilterParams& p, unsigned char* buf, const TileCursor& tc, int type, int py, int px)
 {
     using C = OctetCfg<S>;
     using G = OctetGeom<S>;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float* ug = p.uext + (size_t)frame * p.uext_frame_stride;
-    const int maxc = (int)p.uext_pitch - 1 - ec0;
-    for (int r = warp; r < G::TUH; r += C::NT / 32) {
-        const float* grow = ug + (size_t)min(er0 + r, p.uext_rows - 1) * p.uext_pitch + ec0;
-        const unsigned srow = (unsigned)__cvta_generic_to_shared(buf + r * G::TUW);
-#pragma unroll
-        for (int c = lane; c < G::NCOLS; c += 32) cp_async4(srow + 4u * c, grow + min(c, maxc));
+    const int er0 = S * tc.ty * C::OTH + py;
+    const int ec0 = (S * tc.tx * C::OTW + px) & ~3;
+    const float* ug = p.uext + (size_t)tc.frame * p.uext_frame_stride;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(buf);
+    constexpr int C4 = G::TUW / 4;
+    const int maxc4 = ((int)p.uext_pitch - ec0) / 4 - 1;
+    for (int idx = threadIdx.x; idx < G::TUH * C4; idx += C::NT) {
+        const int r = idx / C4, c4 = idx - r * C4;
+        const float* g = ug + (size_t)min(er0 + r, p.uext_rows - 1) * p.uext_pitch + ec0 + 4 * min(c4, maxc4);
+        cp_async16(sbase + 16u * idx, g);
+    }
+    const uint8_t* hp = p.hash + (size_t)tc.frame * p.hash_frame_stride + (size_t)type * p.hash_plane_stride;
+    constexpr int H16 = C::OTW / 16;
+    const int maxh = ((int)p.hash_pitch - tc.tx * C::OTW) / 16 - 1;
+    for (int idx = threadIdx.x; idx < C::OTH * H16; idx += C::NT) {
+        const int r = idx / H16, c = idx - r * H16;
+        const uint8_t* g = hp + (size_t)min(tc.ty * C::OTH + r, p.oh - 1) * p.hash_pitch + tc.tx * C::OTW + 16 * min(c, maxh);
+        cp_async16(sbase + G::TILE_FLOATS * 4 + 16u * idx, g);
     }
 }
 
@@ -121,8 +155,8 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
     using G = OctetGeom<S>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* tab = reinterpret_cast<float*>(smem_raw);                 // 512-byte records, 128-B aligned
-    float* ubuf0 = tab + (size_t)p.n_buckets * kOctStride;
-    float* ubuf1 = ubuf0 + G::TILE_FLOATS;
+    unsigned char* buf0 = smem_raw + (size_t)max(p.n_buckets, 256) * kOctStride * sizeof(float);
+    unsigned char* buf1 = buf0 + G::BUF_BYTES;
     const int tid = threadIdx.x;
     const int ntypes = S * S;
     const int type = blockIdx.x % ntypes, worker = blockIdx.x / ntypes, nworkers = gridDim.x / ntypes;
@@ -130,20 +164,14 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
     const int lane8 = tid & 7, octet = tid >> 3;
     if ((__cvta_generic_to_shared(tab) & 127) != 0) __trap();  // records must be 128-byte aligned
 
-    const int tiles_per_frame = p.tiles_x * p.tiles_y;
-    const int ntiles = tiles_per_frame * p.n_frames;
-    auto tile_coords = [&](int tile, int& frame, int& oy0, int& ox0) {
-        frame = tile / tiles_per_frame;
-        const int rem = tile - frame * tiles_per_frame;
-        const int ty = rem / p.tiles_x;
-        oy0 = ty * C::OTH;
-        ox0 = (rem - ty * p.tiles_x) * C::OTW;
-    };
-    if (worker < ntiles) {   // first tile in flight while the table slice is copied
-        int f, oy0, ox0;
-        tile_coords(worker, f, oy0, ox0);
-        octet_issue_tile<S>(p, ubuf0, f, S * oy0 + py, S * ox0 + px);
-    }
+    const int ntiles = p.tiles_x * p.tiles_y * p.n_frames;
+    // this octet's item: a warp = 4 consecutive own rows of one segment
+    const int seg = octet / C::OTH, row = octet - seg * C::OTH;
+
+    TileCursor cur, nxt;
+    cur.init(min(worker, max(ntiles - 1, 0)), p.tiles_x, p.tiles_y);
+    nxt = cur;
+    if (worker < ntiles) octet_issue_tile<S>(p, buf0, cur, type, py, px);   // in flight while the table is copied
     cp_async_commit();
     {
         const float4* g = reinterpret_cast<const float4*>(p.table + (size_t)type * p.n_buckets * kOctStride);
@@ -167,86 +195,86 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
     }
     const float4* tab_lane = reinterpret_cast<const float4*>(tab) + lane8;
     const unsigned omask = 0xffu << (tid & 24);  // the eight lanes of this octet
+    const int item_off = (S * row) * G::TUW + S * (seg * C::IW) + px;   // + px: the tile starts at a multiple of 4
 
     int it = 0;
     for (int tile = worker; tile < ntiles; tile += nworkers, ++it) {
-        int frame, oy0, ox0;
-        tile_coords(tile, frame, oy0, ox0);
-        float* ut = (it & 1) ? ubuf1 : ubuf0;
-        if (tile + nworkers < ntiles) {   // prefetch the next tile into the other buffer
-            int f2, oy2, ox2;
-            tile_coords(tile + nworkers, f2, oy2, ox2);
-            octet_issue_tile<S>(p, (it & 1) ? ubuf0 : ubuf1, f2, S * oy2 + py, S * ox2 + px);
-        }
+        unsigned char* buf = (it & 1) ? buf1 : buf0;
+        nxt.advance(nworkers, p.tiles_x, p.tiles_y);
+        if (tile + nworkers < ntiles && !(p.dbg_flags & 4)) octet_issue_tile<S>(p, (it & 1) ? buf0 : buf1, nxt, type, py, px);
         cp_async_commit();
         cp_async_wait<1>();   // everything but the newest group (the prefetch) has landed
         __syncthreads();
 
-        const uint8_t* hplane = p.hash + (size_t)frame * p.hash_frame_stride + (size_t)type * p.hash_plane_stride;
-        OutT* dst = reinterpret_cast<OutT*>(reinterpret_cast<unsigned char*>(p.dst) + (size_t)frame * p.dst_frame_stride);
-
-        for (int item = octet; item < G::ITEMS; item += G::NOCT) {
-            const int seg = item / C::OTH, row = item - seg * C::OTH;   // a warp = 4 consecutive rows
-            const int oy = oy0 + row;
-            const int oxs = ox0 + seg * C::IW;              // first own column of the item
-            if (oy >= p.oh || oxs >= p.ow) continue;         // octet-uniform
-            const uint8_t* hrow = hplane + (size_t)oy * p.hash_pitch + oxs;
-            uint4 hq[C::IW / 16];
-#pragma unroll
-            for (int i = 0; i < C::IW / 16; ++i) hq[i] = __ldg(reinterpret_cast<const uint4*>(hrow) + i);
-            // patch origin of own pixel (row, seg*IW) in the tile
-            const float* base = ut + (S * row) * G::TUW + S * (seg * C::IW);
+        const int oy = cur.ty * C::OTH + row;
+        const int oxs = cur.tx * C::OTW + seg * C::IW;      // first own column of the item
+        if (oy < p.oh && oxs < p.ow) {                      // octet-uniform
+            OutT* drow = reinterpret_cast<OutT*>(reinterpret_cast<unsigned char*>(p.dst) + (size_t)cur.frame * p.dst_frame_stride +
+                                                 (size_t)(S * oy + py) * p.dst_pitch);
+            const float* base = reinterpret_cast<const float*>(buf) + item_off;   // patch origin of the item's first pixel
             const float* pf = base + off_full;
-            float w11[kFlen], w5[5];
-            // windows primed for the virtual pixel one step to the left
+            const uint2* hrow = reinterpret_cast<const uint2*>(buf + G::TILE_FLOATS * 4 + row * C::OTW + seg * C::IW);
+            // circular register windows: element j of pixel i lives in slot (S*i + j) % W
+            float w11[G::WF], w5[G::WP];
 #pragma unroll
-            for (int j = G::NEWF; j < kFlen; ++j) w11[j] = pf[j - S];
+            for (int j = 0; j < G::WF; ++j) w11[j] = 0.0f;
 #pragma unroll
-            for (int t = 0; t < 5; ++t) w5[t] = 0.0f;
+            for (int j = 0; j < G::WP; ++j) w5[j] = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kFlen - G::NEWF; ++j) w11[j] = pf[j];
             if (lane8 < 6) {
                 const float* pp = base + (8 + lane8 / 2) * G::TUW + 5 * (lane8 % 2);
 #pragma unroll
-                for (int t = G::NEWP; t < 5; ++t) w5[t] = pp[t - S];
+                for (int t = 0; t < 5 - G::NEWP; ++t) w5[t] = pp[t];
             }
-            OutT* drow = reinterpret_cast<OutT*>(reinterpret_cast<unsigned char*>(dst) + (size_t)(S * oy + py) * p.dst_pitch);
-            unsigned prev_bucket = 0xffffffffu;
-            float4 t0 = make_float4(0, 0, 0, 0), t1 = t0, t2 = t0, t3 = t0;
-
 #pragma unroll
+            for (int t = 0; t < G::NEWF; ++t) w11[kFlen - G::NEWF + t] = pf[kFlen - G::NEWF + t];
+#pragma unroll
+            for (int t = 0; t < G::NEWP; ++t) w5[5 - G::NEWP + t] = base[off_part[t]];
+            uint2 hb = hrow[0];
+            // taps of the first pixel; afterwards the taps of pixel i+1 are requested before the
+            // FMAs of pixel i (two register sets, even / odd pixel)
+            float4 ta[4], tb[4];
+            {
+                const float4* tp = tab_lane + (hb.x & 0xffu) * (kOctStride / 4);
+                ta[0] = tp[0]; ta[1] = tp[8]; ta[2] = tp[16]; ta[3] = tp[24];
+            }
+#pragma unroll 1
             for (int b0 = 0; b0 < C::IW; b0 += 8) {
                 if (oxs + b0 >= p.ow) break;                  // octet-uniform
-                const uint4 hv = hq[b0 / 16];
-                const unsigned hlo = (b0 & 8) ? hv.z : hv.x, hhi = (b0 & 8) ? hv.w : hv.y;
+                const uint2 hnext = hrow[min(b0 / 8 + 1, C::IW / 8 - 1)];   // hash bytes of the next batch
                 float acc[8];
 #pragma unroll
                 for (int b = 0; b < 8; ++b) {
-                    const int pix = b0 + b;                   // pixel within the item
-                    // slide the windows by S and fetch the fresh patch values
+                    // request the taps of the next pixel
+                    const unsigned nbucket = (b < 7) ? (((b + 1 < 4 ? hb.x : hb.y) >> (8 * ((b + 1) & 3))) & 0xffu) : (hnext.x & 0xffu);
+                    const float4* tp = tab_lane + nbucket * (kOctStride / 4);
+                    float4 (&tc)[4] = (b & 1) ? tb : ta;
+                    float4 (&tn)[4] = (b & 1) ? ta : tb;
+                    tn[0] = tp[0]; tn[1] = tp[8]; tn[2] = tp[16]; tn[3] = tp[24];
+                    // 16 FMAs of this pixel against its windows
+                    constexpr int MP = G::WP - 1;
+                    const int o = S * b;
+                    float a0 = w11[(o + 0) % G::WF] * tc[0].x, a1 = w11[(o + 1) % G::WF] * tc[0].y;
+                    a0 = fmaf(w11[(o + 2) % G::WF], tc[0].z, a0); a1 = fmaf(w11[(o + 3) % G::WF], tc[0].w, a1);
+                    a0 = fmaf(w11[(o + 4) % G::WF], tc[1].x, a0); a1 = fmaf(w11[(o + 5) % G::WF], tc[1].y, a1);
+                    a0 = fmaf(w11[(o + 6) % G::WF], tc[1].z, a0); a1 = fmaf(w11[(o + 7) % G::WF], tc[1].w, a1);
+                    a0 = fmaf(w11[(o + 8) % G::WF], tc[2].x, a0); a1 = fmaf(w11[(o + 9) % G::WF], tc[2].y, a1);
+                    a0 = fmaf(w11[(o + 10) % G::WF], tc[2].z, a0); a1 = fmaf(w5[(o + 0) & MP], tc[2].w, a1);
+                    a0 = fmaf(w5[(o + 1) & MP], tc[3].x, a0); a1 = fmaf(w5[(o + 2) & MP], tc[3].y, a1);
+                    a0 = fmaf(w5[(o + 3) & MP], tc[3].z, a0); a1 = fmaf(w5[(o + 4) & MP], tc[3].w, a1);
+                    // fresh patch values of the next pixel overwrite the slots this pixel has just consumed
+                    const int npix = b0 + b + 1;
+                    if (npix < C::IW && !(p.dbg_flags & 16)) {
+                        const int on = S * (b + 1);
 #pragma unroll
-                    for (int j = 0; j < kFlen - G::NEWF; ++j) w11[j] = w11[j + S];
+                        for (int t = 0; t < G::NEWF; ++t) w11[(on + kFlen - G::NEWF + t) % G::WF] = pf[S * npix + kFlen - G::NEWF + t];
 #pragma unroll
-                    for (int t = 0; t < G::NEWF; ++t) w11[kFlen - G::NEWF + t] = pf[S * pix + kFlen - G::NEWF + t];
-#pragma unroll
-                    for (int t = 0; t < 5 - G::NEWP; ++t) w5[t] = w5[t + S];
-#pragma unroll
-                    for (int t = 0; t < G::NEWP; ++t) w5[5 - G::NEWP + t] = base[S * pix + off_part[t]];
-                    unsigned bucket = ((b < 4 ? hlo : hhi) >> (8 * (b & 3))) & 0xffu;
-                    bucket = min(bucket, (unsigned)(p.n_buckets - 1));
-                    if (bucket != prev_bucket) {              // octet-uniform: neighbours often share a filter
-                        const float4* tp = tab_lane + bucket * (kOctStride / 4);
-                        t0 = tp[0]; t1 = tp[8]; t2 = tp[16]; t3 = tp[24];
-                        prev_bucket = bucket;
+                        for (int t = 0; t < G::NEWP; ++t) w5[(on + 5 - G::NEWP + t) & MP] = base[S * npix + off_part[t]];
                     }
-                    float a0 = w11[0] * t0.x, a1 = w11[1] * t0.y;
-                    a0 = fmaf(w11[2], t0.z, a0); a1 = fmaf(w11[3], t0.w, a1);
-                    a0 = fmaf(w11[4], t1.x, a0); a1 = fmaf(w11[5], t1.y, a1);
-                    a0 = fmaf(w11[6], t1.z, a0); a1 = fmaf(w11[7], t1.w, a1);
-                    a0 = fmaf(w11[8], t2.x, a0); a1 = fmaf(w11[9], t2.y, a1);
-                    a0 = fmaf(w11[10], t2.z, a0); a1 = fmaf(w5[0], t2.w, a1);
-                    a0 = fmaf(w5[1], t3.x, a0); a1 = fmaf(w5[2], t3.y, a1);
-                    a0 = fmaf(w5[3], t3.z, a0); a1 = fmaf(w5[4], t3.w, a1);
                     acc[b] = a0 + a1;
                 }
+                hb = hnext;
                 // transposing butterfly: lane q of the octet ends with the sum of pixel b0+q
                 float r4[4], r2[2];
                 const bool h2 = lane8 & 4, h1 = lane8 & 2, h0 = lane8 & 1;
@@ -266,9 +294,10 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
                 float keep = h0 ? r2[1] : r2[0];
                 float v = keep + __shfl_xor_sync(omask, send, 1);
                 const int ox = oxs + b0 + lane8;
-                if (ox < p.ow) store_px(drow + (S * ox + px), v);
+                if (ox < p.ow && !(p.dbg_flags & 2)) store_px(drow + (S * ox + px), v);
             }
         }
+        cur = nxt;
         __syncthreads();   // tile consumed: its buffer may be refilled by the next prefetch
     }
     cp_async_wait<0>();

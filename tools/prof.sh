@@ -6,5 +6,5 @@ CMD="python bench.py --frames 8 --steps 1 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu1_$TAG.log 2>&1
 $CMD > gpurun_out/plain2_$TAG.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"$KRE" -s 24 -c 2 -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu2_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"$KRE" -s ${3:-24} -c 2 -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu2_$TAG.log 2>&1
 tail -2 gpurun_out/ncu2_$TAG.log
