@@ -7,6 +7,7 @@
 // RAISR_E_CUDA when none is usable.
 #include "../../include/raisr_b200.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -128,7 +129,8 @@ size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Geometry {
     int sw, sh, dw, dh, s;
-    size_t uext_pitch;         // floats
+    size_t uext_pitch;         // floats per image column (uext is stored column-major)
+    size_t uext_cols;          // columns allocated per frame
     size_t uext_frame;         // floats
     size_t hash_pitch, hash_plane, hash_frame;  // bytes
 };
@@ -141,8 +143,9 @@ Geometry make_geometry(int sw, int rows_out, int s)
     g.dw = sw * s;
     g.dh = rows_out;
     g.sh = rows_out / s;
-    g.uext_pitch = round_up((size_t)g.dw + 2 * kMargin + 8, 4);
-    g.uext_frame = g.uext_pitch * (size_t)(rows_out + 2 * kMargin);
+    g.uext_pitch = round_up((size_t)rows_out + 2 * kMargin + 8, 4);
+    g.uext_cols = (size_t)g.dw + 2 * kMargin;
+    g.uext_frame = g.uext_pitch * g.uext_cols;
     g.hash_pitch = round_up((size_t)sw + 16, 16);
     g.hash_plane = g.hash_pitch * (size_t)g.sh;
     g.hash_frame = g.hash_plane * (size_t)(s * s);
@@ -199,20 +202,52 @@ int launch_filter_block(raisr_ctx* h, FilterParams p, cudaStream_t st)
     return 0;
 }
 
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// TMA descriptor of the column-major uext scratch: dims {rows (pitch), columns, frames}, one box =
+// one filter tile (PT rows x NCOLS columns).  The driver entry point is fetched through the runtime,
+// so the library does not link libcuda.
+int make_uext_tmap(CUtensorMap* tm, const FilterParams& p, int box_rows, int box_cols)
+{
+    static PFN_tmapEncodeTiled encode = nullptr;
+    if (!encode) {
+        cudaDriverEntryPointQueryResult q;
+        void* fn = nullptr;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn)
+            return fail(RAISR_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        encode = (PFN_tmapEncodeTiled)fn;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)p.uext_pitch, (cuuint64_t)p.uext_cols, (cuuint64_t)std::max(p.n_frames, 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)p.uext_pitch * sizeof(float), (cuuint64_t)p.uext_frame_stride * sizeof(float)};
+    if (p.n_frames <= 1) strides[1] = (cuuint64_t)p.uext_pitch * p.uext_cols * sizeof(float);
+    cuuint32_t box[3] = {(cuuint32_t)box_rows, (cuuint32_t)box_cols, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)p.uext, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(RAISR_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
 template <int S, typename OutT>
 int launch_filter_octet(raisr_ctx* h, FilterParams p, cudaStream_t st)
 {
     using C = OctetCfg<S>;
+    using G = OctetGeom<S>;
     p.tiles_x = (p.ow + C::OTW - 1) / C::OTW;
     p.tiles_y = (p.oh + C::OTH - 1) / C::OTH;
     size_t smem = octet_smem_bytes<S>(p.n_buckets);
     if (smem > 227 * 1024) return fail(RAISR_E_UNSUPPORTED, "filter table slice of %d buckets does not fit shared memory", p.n_buckets);
+    CUtensorMap tm;
+    if (int rc = make_uext_tmap(&tm, p, G::PT, G::NCOLS)) return rc;
     auto kern = filter_octet_kernel<S, OutT>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int ntypes = S * S;
     long long ntiles = (long long)p.tiles_x * p.tiles_y * p.n_frames;
     int workers = (int)std::max<long long>(1, std::min<long long>(h->sm_count / ntypes, ntiles));
-    kern<<<workers * ntypes, C::NT, smem, st>>>(p);
+    kern<<<workers * ntypes, C::NT, smem, st>>>(p, tm);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -286,6 +321,7 @@ int enqueue_frames(raisr_ctx* h, const uint8_t* dsrc, int sw, int sh, size_t src
         FilterParams fp{};
         fp.uext = pp.uext; fp.uext_pitch = g.uext_pitch; fp.uext_frame_stride = g.uext_frame;
         fp.uext_rows = g.dh + 2 * kMargin;
+        fp.uext_cols = (int)g.uext_cols;
         fp.hash = pp.hash; fp.hash_pitch = g.hash_pitch; fp.hash_plane_stride = g.hash_plane;
         fp.hash_frame_stride = g.hash_frame;
         fp.n_buckets = h->n_buckets;
@@ -657,6 +693,7 @@ int raisr_upsample_band_u8(raisr_t* h, const uint8_t* src_rows_ptr, int sw, int 
     FilterParams fp{};
     fp.uext = pp.uext; fp.uext_pitch = g.uext_pitch; fp.uext_frame_stride = g.uext_frame;
     fp.uext_rows = dst_rows + 2 * kMargin;
+    fp.uext_cols = (int)g.uext_cols;
     fp.hash = pp.hash; fp.hash_pitch = g.hash_pitch; fp.hash_plane_stride = g.hash_plane; fp.hash_frame_stride = g.hash_frame;
     fp.n_buckets = h->n_buckets;
     fp.dst = dst; fp.dst_pitch = dst_pitch; fp.dst_frame_stride = 0;

@@ -22,8 +22,9 @@ constexpr int kRowPad = 12;                    // floats per padded filter row
 constexpr int kFStride = kFlen * kRowPad;      // 132 floats per filter (33 x 16 B: odd -> banks spread)
 
 struct FilterParams {
-    const float* uext;        // (own_rows*S + 10) rows per frame, see raisr_prep.cuh
-    size_t uext_pitch;        // floats, multiple of 4
+    const float* uext;        // (own_rows*S + 10) rows per frame, column-major, see raisr_prep.cuh
+    size_t uext_pitch;        // floats per image column
+    int uext_cols;            // valid columns (dw + 10)
     size_t uext_frame_stride; // floats
     int uext_rows;            // valid rows in uext per frame
     const uint8_t* hash;      // planar by pixel type
@@ -159,12 +160,11 @@ __global__ void __launch_bounds__(BlockCfg<S, OTW, OTH, BR, BC>::NT, 1) filter_b
         const int ec0 = (S * ox0 + px) & ~3;
         const float* ug = p.uext + (size_t)frame * p.uext_frame_stride;
         __syncthreads();  // previous tile fully consumed (also orders the table fill)
-        float4* ut4 = reinterpret_cast<float4*>(ut);
-        for (int idx = tid; idx < C::TUH * (C::TUW / 4); idx += C::NT) {
-            int r = idx / (C::TUW / 4), c4 = idx - r * (C::TUW / 4);
+        for (int idx = tid; idx < C::TUH * C::TUW; idx += C::NT) {
+            int r = idx / C::TUW, c = idx - r * C::TUW;
             int gr = min(er0 + r, p.uext_rows - 1);
-            int gc = min(ec0 + 4 * c4, (int)p.uext_pitch - 4);
-            ut4[idx] = __ldg(reinterpret_cast<const float4*>(ug + (size_t)gr * p.uext_pitch + gc));
+            int gc = min(ec0 + c, p.uext_cols - 1);
+            ut[idx] = __ldg(ug + (size_t)gc * p.uext_pitch + gr);
         }
         __syncthreads();
         if (S == 2) {

@@ -17,6 +17,7 @@
 // transposing butterfly.
 #pragma once
 #include <cstdint>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "raisr_filter.cuh"
@@ -64,11 +65,18 @@ struct OctetCfg<3> { static constexpr int OTW = 64, OTH = 16, IW = 16, NT = 512;
 template <>
 struct OctetCfg<4> { static constexpr int OTW = 32, OTH = 16, IW = 16, NT = 256; };
 
+// The U tile is kept COLUMN-MAJOR in shared memory: element (row r, column c) of the tile at
+// c * PT + r.  The eight lanes of an octet read eight consecutive rows of one column and the four
+// octets of a warp sit on consecutive own rows, so every per-pixel LDS.32 of a warp touches 14
+// consecutive words: conflict-free, and the tile needs no per-thread copy instructions because
+// uext is stored column-major too (raisr_prep.cuh): one TMA box (PT rows x NCOLS columns) per tile.
 template <int S>
 struct OctetGeom {
     using C = OctetCfg<S>;
-    static constexpr int TUH = S * (C::OTH - 1) + kFlen;                              // tile rows
-    static constexpr int TUW = ((S * (C::OTW - 1) + kFlen + (S - 1)) + 3) / 4 * 4;      // tile pitch, 16-byte rows
+    static constexpr int TUH = S * (C::OTH - 1) + kFlen;                 // tile rows needed
+    static constexpr int NCOLS = S * (C::OTW - 1) + kFlen;               // tile columns needed
+    static constexpr int PT = (TUH + 3 + 3) / 4 * 4;                     // floats per tile column (TMA box inner size; the box starts
+                                                                         // at a row multiple of 4: TMA wants 16-byte aligned inner starts)
     static constexpr int NEWF = S;                 // fresh values per pixel in the 11-run
     static constexpr int NEWP = S < 5 ? S : 5;     // fresh values per pixel in the 5-run
     static constexpr int WF = (S == 3) ? 12 : 16;  // circular register window of the 11-run: 8*S % WF == 0
@@ -76,20 +84,20 @@ struct OctetGeom {
     static constexpr int SEGS = C::OTW / C::IW;
     static constexpr int ITEMS = C::OTH * SEGS;
     static constexpr int NOCT = C::NT / 8;
-    static constexpr int TILE_FLOATS = TUH * TUW;
+    static constexpr int TILE_FLOATS = NCOLS * PT;
     static constexpr int HASH_BYTES = C::OTH * C::OTW;   // one byte per own pixel of the tile
-    static constexpr int BUF_BYTES = TILE_FLOATS * 4 + HASH_BYTES;
+    static constexpr int TILE_BYTES = TILE_FLOATS * 4;
+    static constexpr int BUF_BYTES = (TILE_BYTES + HASH_BYTES + 127) / 128 * 128;
     static_assert(C::IW % 8 == 0 && C::OTW % C::IW == 0 && C::OTW % 16 == 0, "items are whole batches of 8 pixels");
-    static_assert((8 * S) % WF == 0 && WF >= kFlen && BUF_BYTES % 16 == 0, "window period / alignment");
-    static_assert(ITEMS == NOCT, "one item per octet and tile");
+    static_assert((8 * S) % WF == 0 && WF >= kFlen && TILE_BYTES % 16 == 0 && NCOLS <= 256 && PT <= 256, "window period / alignment");
+    static_assert(ITEMS == NOCT && (S * C::OTH) % 4 == 0, "one item per octet and tile; tiles start on row quads");
 };
 
 template <int S>
 inline size_t octet_smem_bytes(int n_buckets)
 {
     using G = OctetGeom<S>;
-    size_t table = (size_t)(n_buckets > 256 ? n_buckets : 256) * kOctStride * sizeof(float);  // any hash byte stays inside
-    return table + 2 * (size_t)G::BUF_BYTES;
+    return (size_t)n_buckets * kOctStride * sizeof(float) + 2 * (size_t)G::BUF_BYTES + 16;   // + two mbarriers
 }
 
 __device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gptr)
@@ -120,23 +128,41 @@ struct TileCursor {
     }
 };
 
-// Asynchronous fill of one tile buffer: the U tile (rows er0.., columns ec0.. of the extended
-// upscaled frame, ec0 a multiple of 4) followed by the tile's hash bytes (OTH rows of OTW bytes).
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+
+// Asynchronous fill of one tile buffer.  The U tile (rows S*oy0+py .., columns S*ox0+px .. of the
+// extended upscaled frame, PT x NCOLS, column-major in HBM and in shared memory) is one TMA box
+// issued by a single thread and signalled on an mbarrier; the tile's hash bytes (OTH rows of OTW
+// bytes) follow with 16-byte cp.async.
 template <int S>
-__device__ __forceinline__ void octet_issue_tile(const FilterParams& p, unsigned char* buf, const TileCursor& tc, int type, int py, int px)
+__device__ __forceinline__ void octet_issue_tile(const FilterParams& p, const CUtensorMap* tm, unsigned char* buf, unsigned bar,
+                                                 const TileCursor& tc, int type, int py, int px)
 {
     using C = OctetCfg<S>;
     using G = OctetGeom<S>;
-    const int er0 = S * tc.ty * C::OTH + py;
-    const int ec0 = (S * tc.tx * C::OTW + px) & ~3;
-    const float* ug = p.uext + (size_t)tc.frame * p.uext_frame_stride;
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(buf);
-    constexpr int C4 = G::TUW / 4;
-    const int maxc4 = ((int)p.uext_pitch - ec0) / 4 - 1;
-    for (int idx = threadIdx.x; idx < G::TUH * C4; idx += C::NT) {
-        const int r = idx / C4, c4 = idx - r * C4;
-        const float* g = ug + (size_t)min(er0 + r, p.uext_rows - 1) * p.uext_pitch + ec0 + 4 * min(c4, maxc4);
-        cp_async16(sbase + 16u * idx, g);
+    if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of this buffer are done
+        mbar_expect_tx(bar, G::TILE_BYTES);
+        const int r0 = (S * tc.ty * C::OTH + py) & ~3, c0 = S * tc.tx * C::OTW + px;
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(sbase), "l"(tm), "r"(r0), "r"(c0), "r"(tc.frame), "r"(bar) : "memory");
     }
     const uint8_t* hp = p.hash + (size_t)tc.frame * p.hash_frame_stride + (size_t)type * p.hash_plane_stride;
     constexpr int H16 = C::OTW / 16;
@@ -144,25 +170,32 @@ __device__ __forceinline__ void octet_issue_tile(const FilterParams& p, unsigned
     for (int idx = threadIdx.x; idx < C::OTH * H16; idx += C::NT) {
         const int r = idx / H16, c = idx - r * H16;
         const uint8_t* g = hp + (size_t)min(tc.ty * C::OTH + r, p.oh - 1) * p.hash_pitch + tc.tx * C::OTW + 16 * min(c, maxh);
-        cp_async16(sbase + G::TILE_FLOATS * 4 + 16u * idx, g);
+        cp_async16(sbase + G::TILE_BYTES + 16u * idx, g);
     }
 }
 
 template <int S, typename OutT>
-__global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const FilterParams p)
+__global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const FilterParams p, const __grid_constant__ CUtensorMap tmap)
 {
     using C = OctetCfg<S>;
     using G = OctetGeom<S>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* tab = reinterpret_cast<float*>(smem_raw);                 // 512-byte records, 128-B aligned
-    unsigned char* buf0 = smem_raw + (size_t)max(p.n_buckets, 256) * kOctStride * sizeof(float);
+    unsigned char* buf0 = smem_raw + (size_t)p.n_buckets * kOctStride * sizeof(float);
     unsigned char* buf1 = buf0 + G::BUF_BYTES;
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(buf1 + G::BUF_BYTES), bar1 = bar0 + 8;
     const int tid = threadIdx.x;
     const int ntypes = S * S;
     const int type = blockIdx.x % ntypes, worker = blockIdx.x / ntypes, nworkers = gridDim.x / ntypes;
     const int py = type / S, px = type % S;
     const int lane8 = tid & 7, octet = tid >> 3;
-    if ((__cvta_generic_to_shared(tab) & 127) != 0) __trap();  // records must be 128-byte aligned
+    if ((__cvta_generic_to_shared(tab) & 127) != 0) __trap();  // records and TMA destinations must be 128-byte aligned
+    if (tid == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
     const int ntiles = p.tiles_x * p.tiles_y * p.n_frames;
     // this octet's item: a warp = 4 consecutive own rows of one segment
@@ -171,7 +204,7 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
     TileCursor cur, nxt;
     cur.init(min(worker, max(ntiles - 1, 0)), p.tiles_x, p.tiles_y);
     nxt = cur;
-    if (worker < ntiles) octet_issue_tile<S>(p, buf0, cur, type, py, px);   // in flight while the table is copied
+    if (worker < ntiles) octet_issue_tile<S>(p, &tmap, buf0, bar0, cur, type, py, px);   // in flight while the table is copied
     cp_async_commit();
     {
         const float4* g = reinterpret_cast<const float4*>(p.table + (size_t)type * p.n_buckets * kOctStride);
@@ -179,31 +212,33 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
         for (int i = tid; i < p.n_buckets * (kOctStride / 4); i += C::NT) s[i] = __ldg(g + i);
     }
 
-    // Lane geometry (floats relative to the patch origin of the current pixel in the U tile).
-    const int off_full = lane8 * G::TUW;  // filter row = lane8, column 0
+    // Lane geometry: offsets (floats) from the patch origin of the current pixel in the column-major tile.
+    const int off_full = lane8;           // filter row = lane8, column 0
     int off_part[G::NEWP];                // addresses of the freshly loaded 5-run slots
     if (lane8 < 6) {
 #pragma unroll
         for (int t = 0; t < G::NEWP; ++t)
-            off_part[t] = (8 + lane8 / 2) * G::TUW + 5 * (lane8 % 2) + (5 - G::NEWP) + t;
+            off_part[t] = (8 + lane8 / 2) + (5 * (lane8 % 2) + (5 - G::NEWP) + t) * G::PT;
     } else {
 #pragma unroll
         for (int t = 0; t < G::NEWP; ++t) {
             int idx = (lane8 - 6) * G::NEWP + t;   // leftover taps (8,10) (9,10) (10,10)
-            off_part[t] = (idx < 3 ? (8 + idx) : 10) * G::TUW + 10;
+            off_part[t] = (idx < 3 ? (8 + idx) : 10) + 10 * G::PT;
         }
     }
     const float4* tab_lane = reinterpret_cast<const float4*>(tab) + lane8;
     const unsigned omask = 0xffu << (tid & 24);  // the eight lanes of this octet
-    const int item_off = (S * row) * G::TUW + S * (seg * C::IW) + px;   // + px: the tile starts at a multiple of 4
+    const unsigned maxb = (unsigned)(p.n_buckets - 1);
 
     int it = 0;
     for (int tile = worker; tile < ntiles; tile += nworkers, ++it) {
         unsigned char* buf = (it & 1) ? buf1 : buf0;
         nxt.advance(nworkers, p.tiles_x, p.tiles_y);
-        if (tile + nworkers < ntiles && !(p.dbg_flags & 4)) octet_issue_tile<S>(p, (it & 1) ? buf0 : buf1, nxt, type, py, px);
+        if (tile + nworkers < ntiles && !(p.dbg_flags & 4))
+            octet_issue_tile<S>(p, &tmap, (it & 1) ? buf0 : buf1, (it & 1) ? bar0 : bar1, nxt, type, py, px);
         cp_async_commit();
-        cp_async_wait<1>();   // everything but the newest group (the prefetch) has landed
+        cp_async_wait<1>();   // hash bytes: everything but the newest group (the prefetch) has landed
+        mbar_wait((it & 1) ? bar1 : bar0, (it >> 1) & 1);   // U tile: TMA bytes have landed
         __syncthreads();
 
         const int oy = cur.ty * C::OTH + row;
@@ -211,9 +246,9 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
         if (oy < p.oh && oxs < p.ow) {                      // octet-uniform
             OutT* drow = reinterpret_cast<OutT*>(reinterpret_cast<unsigned char*>(p.dst) + (size_t)cur.frame * p.dst_frame_stride +
                                                  (size_t)(S * oy + py) * p.dst_pitch);
-            const float* base = reinterpret_cast<const float*>(buf) + item_off;   // patch origin of the item's first pixel
+            const float* base = reinterpret_cast<const float*>(buf) + S * (seg * C::IW) * G::PT + S * row + (py & 3);   // S*OTH % 4 == 0
             const float* pf = base + off_full;
-            const uint2* hrow = reinterpret_cast<const uint2*>(buf + G::TILE_FLOATS * 4 + row * C::OTW + seg * C::IW);
+            const uint2* hrow = reinterpret_cast<const uint2*>(buf + G::TILE_BYTES + row * C::OTW + seg * C::IW);
             // circular register windows: element j of pixel i lives in slot (S*i + j) % W
             float w11[G::WF], w5[G::WP];
 #pragma unroll
@@ -221,24 +256,18 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
 #pragma unroll
             for (int j = 0; j < G::WP; ++j) w5[j] = 0.0f;
 #pragma unroll
-            for (int j = 0; j < kFlen - G::NEWF; ++j) w11[j] = pf[j];
+            for (int j = 0; j < kFlen; ++j) w11[j] = pf[j * G::PT];
             if (lane8 < 6) {
-                const float* pp = base + (8 + lane8 / 2) * G::TUW + 5 * (lane8 % 2);
+                const float* pp = base + (8 + lane8 / 2) + 5 * (lane8 % 2) * G::PT;
 #pragma unroll
-                for (int t = 0; t < 5 - G::NEWP; ++t) w5[t] = pp[t];
+                for (int t = 0; t < 5 - G::NEWP; ++t) w5[t] = pp[t * G::PT];
             }
-#pragma unroll
-            for (int t = 0; t < G::NEWF; ++t) w11[kFlen - G::NEWF + t] = pf[kFlen - G::NEWF + t];
 #pragma unroll
             for (int t = 0; t < G::NEWP; ++t) w5[5 - G::NEWP + t] = base[off_part[t]];
             uint2 hb = hrow[0];
-            // taps of the first pixel; afterwards the taps of pixel i+1 are requested before the
-            // FMAs of pixel i (two register sets, even / odd pixel)
-            float4 ta[4], tb[4];
-            {
-                const float4* tp = tab_lane + (hb.x & 0xffu) * (kOctStride / 4);
-                ta[0] = tp[0]; ta[1] = tp[8]; ta[2] = tp[16]; ta[3] = tp[24];
-            }
+            unsigned bucket = min(hb.x & 0xffu, maxb);
+            const float4* tp = tab_lane + bucket * (kOctStride / 4);
+            float4 t0 = tp[0], t1 = tp[8], t2 = tp[16], t3 = tp[24];
 #pragma unroll 1
             for (int b0 = 0; b0 < C::IW; b0 += 8) {
                 if (oxs + b0 >= p.ow) break;                  // octet-uniform
@@ -246,31 +275,35 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
                 float acc[8];
 #pragma unroll
                 for (int b = 0; b < 8; ++b) {
-                    // request the taps of the next pixel
-                    const unsigned nbucket = (b < 7) ? (((b + 1 < 4 ? hb.x : hb.y) >> (8 * ((b + 1) & 3))) & 0xffu) : (hnext.x & 0xffu);
-                    const float4* tp = tab_lane + nbucket * (kOctStride / 4);
-                    float4 (&tc)[4] = (b & 1) ? tb : ta;
-                    float4 (&tn)[4] = (b & 1) ? ta : tb;
-                    tn[0] = tp[0]; tn[1] = tp[8]; tn[2] = tp[16]; tn[3] = tp[24];
-                    // 16 FMAs of this pixel against its windows
+                    // taps of the next pixel: each 16-byte chunk is reloaded as soon as the FMAs of this
+                    // pixel have read it, and only if the next pixel hashes to another bucket
+                    unsigned nbucket = (b < 7) ? (((b + 1 < 4 ? hb.x : hb.y) >> (8 * ((b + 1) & 3))) & 0xffu) : (hnext.x & 0xffu);
+                    nbucket = min(nbucket, maxb);
+                    const bool reload = (nbucket != bucket) || (p.dbg_flags & 1);
+                    bucket = nbucket;
+                    tp = tab_lane + nbucket * (kOctStride / 4);
                     constexpr int MP = G::WP - 1;
                     const int o = S * b;
-                    float a0 = w11[(o + 0) % G::WF] * tc[0].x, a1 = w11[(o + 1) % G::WF] * tc[0].y;
-                    a0 = fmaf(w11[(o + 2) % G::WF], tc[0].z, a0); a1 = fmaf(w11[(o + 3) % G::WF], tc[0].w, a1);
-                    a0 = fmaf(w11[(o + 4) % G::WF], tc[1].x, a0); a1 = fmaf(w11[(o + 5) % G::WF], tc[1].y, a1);
-                    a0 = fmaf(w11[(o + 6) % G::WF], tc[1].z, a0); a1 = fmaf(w11[(o + 7) % G::WF], tc[1].w, a1);
-                    a0 = fmaf(w11[(o + 8) % G::WF], tc[2].x, a0); a1 = fmaf(w11[(o + 9) % G::WF], tc[2].y, a1);
-                    a0 = fmaf(w11[(o + 10) % G::WF], tc[2].z, a0); a1 = fmaf(w5[(o + 0) & MP], tc[2].w, a1);
-                    a0 = fmaf(w5[(o + 1) & MP], tc[3].x, a0); a1 = fmaf(w5[(o + 2) & MP], tc[3].y, a1);
-                    a0 = fmaf(w5[(o + 3) & MP], tc[3].z, a0); a1 = fmaf(w5[(o + 4) & MP], tc[3].w, a1);
+                    float a0 = w11[(o + 0) % G::WF] * t0.x, a1 = w11[(o + 1) % G::WF] * t0.y;
+                    a0 = fmaf(w11[(o + 2) % G::WF], t0.z, a0); a1 = fmaf(w11[(o + 3) % G::WF], t0.w, a1);
+                    if (reload) t0 = tp[0];
+                    a0 = fmaf(w11[(o + 4) % G::WF], t1.x, a0); a1 = fmaf(w11[(o + 5) % G::WF], t1.y, a1);
+                    a0 = fmaf(w11[(o + 6) % G::WF], t1.z, a0); a1 = fmaf(w11[(o + 7) % G::WF], t1.w, a1);
+                    if (reload) t1 = tp[8];
+                    a0 = fmaf(w11[(o + 8) % G::WF], t2.x, a0); a1 = fmaf(w11[(o + 9) % G::WF], t2.y, a1);
+                    a0 = fmaf(w11[(o + 10) % G::WF], t2.z, a0); a1 = fmaf(w5[(o + 0) & MP], t2.w, a1);
+                    if (reload) t2 = tp[16];
+                    a0 = fmaf(w5[(o + 1) & MP], t3.x, a0); a1 = fmaf(w5[(o + 2) & MP], t3.y, a1);
+                    a0 = fmaf(w5[(o + 3) & MP], t3.z, a0); a1 = fmaf(w5[(o + 4) & MP], t3.w, a1);
+                    if (reload) t3 = tp[24];
                     // fresh patch values of the next pixel overwrite the slots this pixel has just consumed
                     const int npix = b0 + b + 1;
                     if (npix < C::IW && !(p.dbg_flags & 16)) {
                         const int on = S * (b + 1);
 #pragma unroll
-                        for (int t = 0; t < G::NEWF; ++t) w11[(on + kFlen - G::NEWF + t) % G::WF] = pf[S * npix + kFlen - G::NEWF + t];
+                        for (int t = 0; t < G::NEWF; ++t) w11[(on + kFlen - G::NEWF + t) % G::WF] = pf[(S * npix + kFlen - G::NEWF + t) * G::PT];
 #pragma unroll
-                        for (int t = 0; t < G::NEWP; ++t) w5[(on + 5 - G::NEWP + t) & MP] = base[S * npix + off_part[t]];
+                        for (int t = 0; t < G::NEWP; ++t) w5[(on + 5 - G::NEWP + t) & MP] = base[S * npix * G::PT + off_part[t]];
                     }
                     acc[b] = a0 + a1;
                 }
