@@ -128,6 +128,18 @@ struct TileCursor {
     }
 };
 
+// Predicated in-place 128-bit shared load: t is overwritten only when `pred` is set (no register
+// renaming / move chains around the conditional reload of the tap registers).
+__device__ __forceinline__ void lds128_if(float4& t, unsigned saddr, bool pred)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %5, 0;\n\t"
+        "@p ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+        : "+f"(t.x), "+f"(t.y), "+f"(t.z), "+f"(t.w)
+        : "r"(saddr), "r"((unsigned)pred));
+}
+
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -227,6 +239,7 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
         }
     }
     const float4* tab_lane = reinterpret_cast<const float4*>(tab) + lane8;
+    const unsigned tab_lane_s = (unsigned)__cvta_generic_to_shared(tab_lane);
     const unsigned omask = 0xffu << (tid & 24);  // the eight lanes of this octet
     const unsigned maxb = (unsigned)(p.n_buckets - 1);
 
@@ -281,21 +294,21 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
                     nbucket = min(nbucket, maxb);
                     const bool reload = (nbucket != bucket) || (p.dbg_flags & 1);
                     bucket = nbucket;
-                    tp = tab_lane + nbucket * (kOctStride / 4);
+                    const unsigned tpa = tab_lane_s + nbucket * (kOctStride * 4);
                     constexpr int MP = G::WP - 1;
                     const int o = S * b;
                     float a0 = w11[(o + 0) % G::WF] * t0.x, a1 = w11[(o + 1) % G::WF] * t0.y;
                     a0 = fmaf(w11[(o + 2) % G::WF], t0.z, a0); a1 = fmaf(w11[(o + 3) % G::WF], t0.w, a1);
-                    if (reload) t0 = tp[0];
+                    lds128_if(t0, tpa, reload);
                     a0 = fmaf(w11[(o + 4) % G::WF], t1.x, a0); a1 = fmaf(w11[(o + 5) % G::WF], t1.y, a1);
                     a0 = fmaf(w11[(o + 6) % G::WF], t1.z, a0); a1 = fmaf(w11[(o + 7) % G::WF], t1.w, a1);
-                    if (reload) t1 = tp[8];
+                    lds128_if(t1, tpa + 128, reload);
                     a0 = fmaf(w11[(o + 8) % G::WF], t2.x, a0); a1 = fmaf(w11[(o + 9) % G::WF], t2.y, a1);
                     a0 = fmaf(w11[(o + 10) % G::WF], t2.z, a0); a1 = fmaf(w5[(o + 0) & MP], t2.w, a1);
-                    if (reload) t2 = tp[16];
+                    lds128_if(t2, tpa + 256, reload);
                     a0 = fmaf(w5[(o + 1) & MP], t3.x, a0); a1 = fmaf(w5[(o + 2) & MP], t3.y, a1);
                     a0 = fmaf(w5[(o + 3) & MP], t3.z, a0); a1 = fmaf(w5[(o + 4) & MP], t3.w, a1);
-                    if (reload) t3 = tp[24];
+                    lds128_if(t3, tpa + 384, reload);
                     // fresh patch values of the next pixel overwrite the slots this pixel has just consumed
                     const int npix = b0 + b + 1;
                     if (npix < C::IW && !(p.dbg_flags & 16)) {
