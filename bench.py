@@ -128,6 +128,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--filter-impl", type=int, default=None, help="1 octet (default), 0 block")
     ap.add_argument("--dbg-flags", type=int, default=0, help="kernel timing experiments (results invalid)")
+    ap.add_argument("--overlap", type=int, default=None, help="1: overlapped prep/filter pipeline, 0: serial")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -152,6 +153,8 @@ def main():
         r.set_option("filter_impl", args.filter_impl)
     if args.dbg_flags:
         r.set_option("dbg_flags", args.dbg_flags)
+    if args.overlap is not None:
+        r.set_option("overlap", args.overlap)
     info = r.device_info()
     n = args.frames
     dw, dh = SW * SCALE, SH * SCALE

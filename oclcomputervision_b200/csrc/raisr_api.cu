@@ -90,6 +90,9 @@ struct raisr_ctx {
     bool use_user_stream = false;
     ScaleTable tables[5];  // index = scale (2..4)
     DevBuf uext, hash, dsrc[2], ddst[2], dbg;
+    DevBuf uext2, hash2;          // second scratch set of the overlapped pipeline
+    cudaStream_t prep_stream = nullptr, filt_stream = nullptr;
+    int overlap = 0;              // 1: prep of chunk c+1 shares the SMs with the filter of chunk c
     std::vector<cudaEvent_t> ev_pool;
     long long launches = 0;
     float last_prep_ms = 0, last_filter_ms = 0;
@@ -153,28 +156,33 @@ Geometry make_geometry(int sw, int rows_out, int s)
 }
 
 template <int S, bool DBG, int NQ>
-void launch_prep_q(const PrepParams& p, cudaStream_t st)
+void launch_prep_q(PrepParams p, cudaStream_t st, int max_ctas)
 {
-    dim3 grid((p.dw + PT_W - 1) / PT_W, (p.rows + PT_H - 1) / PT_H, p.n_frames);
+    p.tiles_x = (p.dw + PT_W - 1) / PT_W;
+    p.tiles_y = (p.rows + PT_H - 1) / PT_H;
+    long long total = (long long)p.tiles_x * p.tiles_y * p.n_frames;
+    int grid = (int)std::max<long long>(1, std::min<long long>(total, max_ctas));
     size_t smem = sizeof(PrepSmem);
     cudaFuncSetAttribute(prep_kernel<S, DBG, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     prep_kernel<S, DBG, NQ><<<grid, PT_THREADS, smem, st>>>(p);
 }
 
 template <int S>
-void launch_prep_t(const PrepParams& p, cudaStream_t st, bool dbg)
+void launch_prep_t(const PrepParams& p, cudaStream_t st, bool dbg, int max_ctas)
 {
     const bool small = p.n_strength <= 3 && p.n_coherence <= 3;   // the reference's 3 x 3 (raisr.cl:9-15)
-    if (dbg) small ? launch_prep_q<S, true, 2>(p, st) : launch_prep_q<S, true, kMaxQ>(p, st);
-    else small ? launch_prep_q<S, false, 2>(p, st) : launch_prep_q<S, false, kMaxQ>(p, st);
+    if (dbg) small ? launch_prep_q<S, true, 2>(p, st, max_ctas) : launch_prep_q<S, true, kMaxQ>(p, st, max_ctas);
+    else small ? launch_prep_q<S, false, 2>(p, st, max_ctas) : launch_prep_q<S, false, kMaxQ>(p, st, max_ctas);
 }
 
-int launch_prep(raisr_ctx* h, const PrepParams& p, int s, cudaStream_t st, bool dbg)
+// ctas_per_sm == 0: one CTA per tile (the hardware scheduler balances); > 0: persistent grid of that many CTAs per SM
+int launch_prep(raisr_ctx* h, const PrepParams& p, int s, cudaStream_t st, bool dbg, int ctas_per_sm = 0)
 {
+    const int max_ctas = ctas_per_sm > 0 ? h->sm_count * ctas_per_sm : 0x7fffffff;
     switch (s) {
-    case 2: launch_prep_t<2>(p, st, dbg); break;
-    case 3: launch_prep_t<3>(p, st, dbg); break;
-    case 4: launch_prep_t<4>(p, st, dbg); break;
+    case 2: launch_prep_t<2>(p, st, dbg, max_ctas); break;
+    case 3: launch_prep_t<3>(p, st, dbg, max_ctas); break;
+    case 4: launch_prep_t<4>(p, st, dbg, max_ctas); break;
     default: return fail(RAISR_E_UNSUPPORTED, "scale %d not supported (2, 3 or 4)", s);
     }
     h->launches++;
@@ -231,18 +239,18 @@ int make_uext_tmap(CUtensorMap* tm, const FilterParams& p, int box_rows, int box
     return 0;
 }
 
-template <int S, typename OutT>
+template <int S, typename OutT, int NBUF>
 int launch_filter_octet(raisr_ctx* h, FilterParams p, cudaStream_t st)
 {
     using C = OctetCfg<S>;
     using G = OctetGeom<S>;
     p.tiles_x = (p.ow + C::OTW - 1) / C::OTW;
     p.tiles_y = (p.oh + C::OTH - 1) / C::OTH;
-    size_t smem = octet_smem_bytes<S>(p.n_buckets);
+    size_t smem = octet_smem_bytes<S, NBUF>(p.n_buckets);
     if (smem > 227 * 1024) return fail(RAISR_E_UNSUPPORTED, "filter table slice of %d buckets does not fit shared memory", p.n_buckets);
     CUtensorMap tm;
     if (int rc = make_uext_tmap(&tm, p, G::PT, G::NCOLS)) return rc;
-    auto kern = filter_octet_kernel<S, OutT>;
+    auto kern = filter_octet_kernel<S, OutT, NBUF>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int ntypes = S * S;
     long long ntiles = (long long)p.tiles_x * p.tiles_y * p.n_frames;
@@ -254,16 +262,23 @@ int launch_filter_octet(raisr_ctx* h, FilterParams p, cudaStream_t st)
 }
 
 template <typename OutT>
-int launch_filter(raisr_ctx* h, FilterParams p, int s, cudaStream_t st)
+int launch_filter(raisr_ctx* h, FilterParams p, int s, cudaStream_t st, bool single_buffer = false)
 {
     ScaleTable& t = h->tables[s];
     p.dbg_flags = h->dbg_flags;
     if (h->filter_impl == 1) {
         p.table = (const float*)t.octet.p;
+        if (single_buffer) {
+            switch (s) {
+            case 2: return launch_filter_octet<2, OutT, 1>(h, p, st);
+            case 3: return launch_filter_octet<3, OutT, 1>(h, p, st);
+            case 4: return launch_filter_octet<4, OutT, 1>(h, p, st);
+            }
+        }
         switch (s) {
-        case 2: return launch_filter_octet<2, OutT>(h, p, st);
-        case 3: return launch_filter_octet<3, OutT>(h, p, st);
-        case 4: return launch_filter_octet<4, OutT>(h, p, st);
+        case 2: return launch_filter_octet<2, OutT, 2>(h, p, st);
+        case 3: return launch_filter_octet<3, OutT, 2>(h, p, st);
+        case 4: return launch_filter_octet<4, OutT, 2>(h, p, st);
         }
     } else {
         p.table = (const float*)t.block.p;
@@ -295,7 +310,34 @@ int check_common(raisr_ctx* h, const void* src, int sw, int sh, size_t src_pitch
     return 0;
 }
 
-// Enqueue prep+filter for `nf` frames that are already on the device.
+void fill_params(raisr_ctx* h, const Geometry& g, const uint8_t* dsrc, int sw, int sh, size_t src_pitch, void* ddst, size_t dst_pitch,
+                 int scale, int f0, int n, float* uext, uint8_t* hash, PrepParams& pp, FilterParams& fp)
+{
+    pp = PrepParams{};
+    pp.src = dsrc + (size_t)f0 * src_pitch * sh;
+    pp.src_pitch = src_pitch;
+    pp.src_frame_stride = src_pitch * sh;
+    pp.sw = sw; pp.sh_glob = sh; pp.src_row0 = 0; pp.src_rows = sh;
+    pp.dw = g.dw; pp.dh_glob = g.dh; pp.y0 = 0; pp.rows = g.dh; pp.n_frames = n;
+    pp.uext = uext; pp.uext_pitch = g.uext_pitch; pp.uext_frame_stride = g.uext_frame;
+    pp.hash = hash; pp.hash_pitch = g.hash_pitch; pp.hash_plane_stride = g.hash_plane;
+    pp.hash_frame_stride = g.hash_frame;
+    pp.n_angle = h->n_angle; pp.n_strength = h->n_strength; pp.n_coherence = h->n_coherence;
+    memcpy(pp.sq, h->sq, sizeof(pp.sq)); memcpy(pp.cq, h->cq, sizeof(pp.cq));
+    fp = FilterParams{};
+    fp.uext = pp.uext; fp.uext_pitch = g.uext_pitch; fp.uext_frame_stride = g.uext_frame;
+    fp.uext_rows = g.dh + 2 * kMargin;
+    fp.uext_cols = (int)g.uext_cols;
+    fp.hash = pp.hash; fp.hash_pitch = g.hash_pitch; fp.hash_plane_stride = g.hash_plane;
+    fp.hash_frame_stride = g.hash_frame;
+    fp.n_buckets = h->n_buckets;
+    fp.dst = (unsigned char*)ddst + (size_t)f0 * dst_pitch * g.dh;
+    fp.dst_pitch = dst_pitch; fp.dst_frame_stride = dst_pitch * g.dh;
+    fp.ow = sw; fp.oh = sh; fp.n_frames = n;
+}
+
+// Enqueue prep+filter for `nf` frames that are already on the device.  Event slots used (relative to
+// ev_base): 3 per chunk in the serial pipeline; the overlapped pipeline uses 4 per chunk + 2.
 template <typename OutT>
 int enqueue_frames(raisr_ctx* h, const uint8_t* dsrc, int sw, int sh, size_t src_pitch, OutT* ddst,
                    size_t dst_pitch, int scale, int nf, cudaStream_t st, bool timed, size_t ev_base)
@@ -305,29 +347,42 @@ int enqueue_frames(raisr_ctx* h, const uint8_t* dsrc, int sw, int sh, size_t src
     int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nf, h->chunk_budget / std::max<size_t>(per_frame, 1)));
     if (int rc = h->uext.ensure(per_frame * chunk)) return rc;
     if (int rc = h->hash.ensure(g.hash_frame * chunk)) return rc;
+    const int nchunks = (nf + chunk - 1) / chunk;
+    PrepParams pp;
+    FilterParams fp;
+    if (h->overlap && h->filter_impl == 1 && nchunks > 1) {
+        // Overlapped pipeline: the prep kernel (instruction-issue bound) of chunk c+1 runs as one
+        // persistent CTA per SM next to the single-buffered filter kernel (shared-memory-pipe bound)
+        // of chunk c.  Two scratch sets, two internal streams, the filter stream has priority so that
+        // its CTAs are placed first when both kernels become runnable together.
+        if (int rc = h->uext2.ensure(per_frame * chunk)) return rc;
+        if (int rc = h->hash2.ensure(g.hash_frame * chunk)) return rc;
+        cudaStream_t sp = h->prep_stream, sf = h->filt_stream;
+        auto E = [&](int c, int k) { return h->ev(ev_base + 2 + (size_t)c * 4 + k); };   // 0/1 prep start/stop, 2/3 filter start/stop
+        cudaEventRecord(h->ev(ev_base), st);
+        cudaStreamWaitEvent(sp, h->ev(ev_base), 0);
+        cudaStreamWaitEvent(sf, h->ev(ev_base), 0);
+        for (int c = 0; c < nchunks; ++c) {
+            const int f0 = c * chunk, n = std::min(chunk, nf - f0), b = c & 1;
+            fill_params(h, g, dsrc, sw, sh, src_pitch, ddst, dst_pitch, scale, f0, n, (float*)(b ? h->uext2.p : h->uext.p),
+                        (uint8_t*)(b ? h->hash2.p : h->hash.p), pp, fp);
+            if (c >= 2) cudaStreamWaitEvent(sp, E(c - 2, 3), 0);   // scratch set b is free again
+            cudaEventRecord(E(c, 0), sp);
+            if (int rc = launch_prep(h, pp, scale, sp, false, c == 0 ? 0 : 1)) return rc;
+            cudaEventRecord(E(c, 1), sp);
+            cudaStreamWaitEvent(sf, E(c, 1), 0);
+            cudaEventRecord(E(c, 2), sf);
+            if (int rc = launch_filter<OutT>(h, fp, scale, sf, true)) return rc;
+            cudaEventRecord(E(c, 3), sf);
+        }
+        cudaStreamWaitEvent(st, E(nchunks - 1, 3), 0);
+        cudaStreamWaitEvent(st, E(nchunks - 1, 1), 0);
+        cudaEventRecord(h->ev(ev_base + 1), st);
+        return -1000 - nchunks;   // overlapped: caller reads the event layout above
+    }
     for (int f0 = 0; f0 < nf; f0 += chunk) {
         int n = std::min(chunk, nf - f0);
-        PrepParams pp{};
-        pp.src = dsrc + (size_t)f0 * src_pitch * sh;
-        pp.src_pitch = src_pitch;
-        pp.src_frame_stride = src_pitch * sh;
-        pp.sw = sw; pp.sh_glob = sh; pp.src_row0 = 0; pp.src_rows = sh;
-        pp.dw = g.dw; pp.dh_glob = g.dh; pp.y0 = 0; pp.rows = g.dh; pp.n_frames = n;
-        pp.uext = (float*)h->uext.p; pp.uext_pitch = g.uext_pitch; pp.uext_frame_stride = g.uext_frame;
-        pp.hash = (uint8_t*)h->hash.p; pp.hash_pitch = g.hash_pitch; pp.hash_plane_stride = g.hash_plane;
-        pp.hash_frame_stride = g.hash_frame;
-        pp.n_angle = h->n_angle; pp.n_strength = h->n_strength; pp.n_coherence = h->n_coherence;
-        memcpy(pp.sq, h->sq, sizeof(pp.sq)); memcpy(pp.cq, h->cq, sizeof(pp.cq));
-        FilterParams fp{};
-        fp.uext = pp.uext; fp.uext_pitch = g.uext_pitch; fp.uext_frame_stride = g.uext_frame;
-        fp.uext_rows = g.dh + 2 * kMargin;
-        fp.uext_cols = (int)g.uext_cols;
-        fp.hash = pp.hash; fp.hash_pitch = g.hash_pitch; fp.hash_plane_stride = g.hash_plane;
-        fp.hash_frame_stride = g.hash_frame;
-        fp.n_buckets = h->n_buckets;
-        fp.dst = (unsigned char*)ddst + (size_t)f0 * dst_pitch * g.dh;
-        fp.dst_pitch = dst_pitch; fp.dst_frame_stride = dst_pitch * g.dh;
-        fp.ow = sw; fp.oh = sh; fp.n_frames = n;
+        fill_params(h, g, dsrc, sw, sh, src_pitch, ddst, dst_pitch, scale, f0, n, (float*)h->uext.p, (uint8_t*)h->hash.p, pp, fp);
         size_t e = ev_base + 3 * (size_t)(f0 / chunk);
         if (timed) cudaEventRecord(h->ev(e), st);
         if (int rc = launch_prep(h, pp, scale, st, false)) return rc;
@@ -335,7 +390,31 @@ int enqueue_frames(raisr_ctx* h, const uint8_t* dsrc, int sw, int sh, size_t src
         if (int rc = launch_filter<OutT>(h, fp, scale, st)) return rc;
         if (timed) cudaEventRecord(h->ev(e + 2), st);
     }
-    return (nf + chunk - 1) / chunk;  // number of chunks (>0)
+    return nchunks;  // number of chunks (>0)
+}
+
+// Kernel times of the last enqueue_frames() call from its events (after the stream has been synchronised).
+void read_kernel_times(raisr_ctx* h, int rc, size_t ev_base, float* prep, float* filt)
+{
+    *prep = *filt = 0;
+    if (rc <= -1000) {   // overlapped: per-kernel wall durations overlap in time; filt is reported as total - nothing hidden
+        const int nchunks = -1000 - rc;
+        float total = 0;
+        cudaEventElapsedTime(&total, h->ev(ev_base), h->ev(ev_base + 1));
+        for (int c = 0; c < nchunks; ++c) {
+            float a = 0;
+            cudaEventElapsedTime(&a, h->ev(ev_base + 2 + (size_t)c * 4), h->ev(ev_base + 2 + (size_t)c * 4 + 1));
+            *prep += a;
+        }
+        *filt = total;   // wall time of the whole overlapped section
+        return;
+    }
+    for (int c = 0; c < rc; ++c) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, h->ev(ev_base + 3 * c), h->ev(ev_base + 3 * c + 1));
+        cudaEventElapsedTime(&b, h->ev(ev_base + 3 * c + 1), h->ev(ev_base + 3 * c + 2));
+        *prep += a; *filt += b;
+    }
 }
 
 template <typename OutT>
@@ -347,18 +426,13 @@ int upsample_impl(raisr_ctx* h, const uint8_t* src, int sw, int sh, size_t src_p
     if (where == RAISR_DEVICE) {
         cudaStream_t st = h->stream();
         int nchunks = enqueue_frames<OutT>(h, src, sw, sh, src_pitch, dst, dst_pitch, scale, n_frames, st, ms != nullptr, 0);
-        if (nchunks < 0) return nchunks;
+        if (nchunks < 0 && nchunks > -1000) return nchunks;
         if (ms) {
             CUDA_TRY(cudaStreamSynchronize(st));
             float prep = 0, filt = 0;
-            for (int c = 0; c < nchunks; ++c) {
-                float a = 0, b = 0;
-                cudaEventElapsedTime(&a, h->ev(3 * c), h->ev(3 * c + 1));
-                cudaEventElapsedTime(&b, h->ev(3 * c + 1), h->ev(3 * c + 2));
-                prep += a; filt += b;
-            }
+            read_kernel_times(h, nchunks, 0, &prep, &filt);
             h->last_prep_ms = prep; h->last_filter_ms = filt;
-            ms[0] = 0; ms[1] = prep + filt; ms[2] = 0;
+            ms[0] = 0; ms[1] = nchunks <= -1000 ? filt : prep + filt; ms[2] = 0;
         }
         return 0;
     }
@@ -368,15 +442,18 @@ int upsample_impl(raisr_ctx* h, const uint8_t* src, int sw, int sh, size_t src_p
     const size_t src_frame = src_pitch * sh, dst_frame = dst_pitch * dh;
     Geometry g = make_geometry(sw, dh, scale);
     size_t per_frame = g.uext_frame * sizeof(float);
-    int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_frames, h->chunk_budget / std::max<size_t>(per_frame, 1)));
+    int dev_chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_frames, h->chunk_budget / std::max<size_t>(per_frame, 1)));
+    // with the overlapped kernel pipeline a host chunk spans several device chunks so that it has something to overlap
+    int chunk = std::min(n_frames, h->overlap ? dev_chunk * 4 : dev_chunk);
     for (int b = 0; b < 2; ++b) {
         if (int rc = h->dsrc[b].ensure(src_frame * chunk)) return rc;
         if (int rc = h->ddst[b].ensure(dst_frame * chunk)) return rc;
     }
     cudaStream_t sc = h->own_stream, sh2d = h->h2d_stream, sd2h = h->d2h_stream;
     const int nchunks = (n_frames + chunk - 1) / chunk;
-    // events: per chunk 9 = h2d start/stop, prep start/mid/stop (3), d2h start/stop, spare
-    auto E = [&](int c, int k) { return h->ev(16 + (size_t)c * 8 + k); };
+    // 64 event slots per host chunk: 0/1 H2D, 2/3 D2H, 4 kernels done, 8.. kernel events of enqueue_frames
+    auto E = [&](int c, int k) { return h->ev(16 + (size_t)c * 64 + k); };
+    std::vector<int> krc(nchunks, 0);
     for (int c = 0; c < nchunks; ++c) {
         const int b = c & 1, f0 = c * chunk, n = std::min(chunk, n_frames - f0);
         if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(sh2d, E(c - 2, 4), 0));  // kernels of chunk c-2 done with dsrc[b]
@@ -384,29 +461,31 @@ int upsample_impl(raisr_ctx* h, const uint8_t* src, int sw, int sh, size_t src_p
         CUDA_TRY(cudaMemcpyAsync(h->dsrc[b].p, src + (size_t)f0 * src_frame, src_frame * n, cudaMemcpyHostToDevice, sh2d));
         CUDA_TRY(cudaEventRecord(E(c, 1), sh2d));
         CUDA_TRY(cudaStreamWaitEvent(sc, E(c, 1), 0));
-        if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(sc, E(c - 2, 6), 0));    // D2H of chunk c-2 done with ddst[b]
-        // enqueue_frames records 3 events at ev_base.. : reuse slots 2,3,4 of this chunk
+        if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(sc, E(c - 2, 3), 0));    // D2H of chunk c-2 done with ddst[b]
         int rc = enqueue_frames<OutT>(h, (const uint8_t*)h->dsrc[b].p, sw, sh, src_pitch, (OutT*)h->ddst[b].p, dst_pitch,
-                                      scale, n, sc, true, 16 + (size_t)c * 8 + 2);
-        if (rc < 0) return rc;
+                                      scale, n, sc, true, 16 + (size_t)c * 64 + 8);
+        if (rc < 0 && rc > -1000) return rc;
+        krc[c] = rc;
+        CUDA_TRY(cudaEventRecord(E(c, 4), sc));
         CUDA_TRY(cudaStreamWaitEvent(sd2h, E(c, 4), 0));
-        CUDA_TRY(cudaEventRecord(E(c, 5), sd2h));
+        CUDA_TRY(cudaEventRecord(E(c, 2), sd2h));
         CUDA_TRY(cudaMemcpyAsync((unsigned char*)dst + (size_t)f0 * dst_frame, h->ddst[b].p, dst_frame * n, cudaMemcpyDeviceToHost, sd2h));
-        CUDA_TRY(cudaEventRecord(E(c, 6), sd2h));
+        CUDA_TRY(cudaEventRecord(E(c, 3), sd2h));
     }
     CUDA_TRY(cudaStreamSynchronize(sd2h));
     CUDA_TRY(cudaStreamSynchronize(sc));
     CUDA_TRY(cudaStreamSynchronize(sh2d));
-    float t_h2d = 0, t_prep = 0, t_filt = 0, t_d2h = 0;
+    float t_h2d = 0, t_prep = 0, t_filt = 0, t_d2h = 0, t_kern = 0;
     for (int c = 0; c < nchunks; ++c) {
-        float a = 0;
+        float a = 0, p1 = 0, f1 = 0;
         cudaEventElapsedTime(&a, E(c, 0), E(c, 1)); t_h2d += a;
-        cudaEventElapsedTime(&a, E(c, 2), E(c, 3)); t_prep += a;
-        cudaEventElapsedTime(&a, E(c, 3), E(c, 4)); t_filt += a;
-        cudaEventElapsedTime(&a, E(c, 5), E(c, 6)); t_d2h += a;
+        cudaEventElapsedTime(&a, E(c, 2), E(c, 3)); t_d2h += a;
+        read_kernel_times(h, krc[c], 16 + (size_t)c * 64 + 8, &p1, &f1);
+        t_prep += p1; t_filt += f1;
+        t_kern += krc[c] <= -1000 ? f1 : p1 + f1;
     }
     h->last_prep_ms = t_prep; h->last_filter_ms = t_filt;
-    if (ms) { ms[0] = t_h2d; ms[1] = t_prep + t_filt; ms[2] = t_d2h; }
+    if (ms) { ms[0] = t_h2d; ms[1] = t_kern; ms[2] = t_d2h; }
     return 0;
 }
 
@@ -470,6 +549,15 @@ int raisr_create(raisr_t** out, int device, int n_angle, int n_strength, int n_c
         delete h;
         return fail(RAISR_E_CUDA, "cudaStreamCreate failed");
     }
+    {
+        int lo = 0, hi = 0;   // numerically lower = higher priority
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&h->filt_stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&h->prep_stream, cudaStreamNonBlocking, lo) != cudaSuccess) {
+            delete h;
+            return fail(RAISR_E_CUDA, "cudaStreamCreateWithPriority failed");
+        }
+    }
     const char* impl = getenv("RAISR_FILTER_IMPL");
     if (impl && !strcmp(impl, "block")) h->filter_impl = 0;
     *out = h;
@@ -482,7 +570,9 @@ void raisr_destroy(raisr_t* h)
     Guard guard(h->device);
     cudaDeviceSynchronize();
     for (auto& t : h->tables) { t.block.release(); t.octet.release(); }
-    h->uext.release(); h->hash.release(); h->dbg.release();
+    h->uext.release(); h->hash.release(); h->dbg.release(); h->uext2.release(); h->hash2.release();
+    if (h->prep_stream) cudaStreamDestroy(h->prep_stream);
+    if (h->filt_stream) cudaStreamDestroy(h->filt_stream);
     for (int b = 0; b < 2; ++b) { h->dsrc[b].release(); h->ddst[b].release(); }
     for (auto e : h->ev_pool) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -541,6 +631,7 @@ int raisr_set_option(raisr_t* h, const char* key, long long value)
     if (!h || !key) return fail(RAISR_E_ARG, "null argument");
     if (!strcmp(key, "filter_impl")) { h->filter_impl = value ? 1 : 0; return 0; }
     if (!strcmp(key, "dbg_flags")) { h->dbg_flags = (int)value; return 0; }
+    if (!strcmp(key, "overlap")) { h->overlap = value ? 1 : 0; return 0; }
     if (!strcmp(key, "chunk_budget_bytes")) { h->chunk_budget = (size_t)std::max<long long>(value, 1 << 20); return 0; }
     return fail(RAISR_E_ARG, "unknown option %s", key);
 }

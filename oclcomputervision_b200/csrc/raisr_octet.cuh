@@ -25,12 +25,16 @@
 namespace raisr {
 
 constexpr int kOctStride = 128;  // floats per filter record (512 B)
+// Rows 8..10 of the filter are split into two 5-runs (columns kRunCol0.. and kRunCol0+5..) and one
+// leftover tap (column kSingleCol); this split leaves the fewest shared-memory bank conflicts on the
+// per-pixel loads of the 5-runs for the tile pitches in use (searched offline).
+constexpr int kRunCol0 = 1, kSingleCol = 0;
 
 // Host-side packing of one 11x11 filter (row-major taps f[i*11+j]) into the lane-major record:
 // record float (p + 8n)*4 + c  <->  slot s = 4n + c of lane p.
 //   slots 0..10  : filter row p, columns 0..10            (p = 0..7)
-//   slots 11..15 : lanes 0..5: row 8 + p/2, columns 5*(p%2) .. +4
-//                  lanes 6,7 : the three leftover taps (8,10) (9,10) (10,10) in the slots that are
+//   slots 11..15 : lanes 0..5: row 8 + p/2, columns 1 + 5*(p%2) .. +4
+//                  lanes 6,7 : the three leftover taps (8,0) (9,0) (10,0) in the slots that are
 //                              freshly loaded for every pixel (the last min(S,5) slots); which
 //                              ones depends on S, so the record is packed per scale.
 inline void octet_single_slot(int S, int idx, int* lane, int* slot)
@@ -47,11 +51,11 @@ inline void octet_pack_filter_s(const float* f, float* rec, int S)
     for (int p = 0; p < 8; ++p)
         for (int j = 0; j < kFlen; ++j) put(p, j, f[p * kFlen + j]);
     for (int p = 0; p < 6; ++p)
-        for (int t = 0; t < 5; ++t) put(p, 11 + t, f[(8 + p / 2) * kFlen + 5 * (p % 2) + t]);
+        for (int t = 0; t < 5; ++t) put(p, 11 + t, f[(8 + p / 2) * kFlen + kRunCol0 + 5 * (p % 2) + t]);
     for (int idx = 0; idx < 3; ++idx) {
         int lane, slot;
         octet_single_slot(S, idx, &lane, &slot);
-        put(lane, slot, f[(8 + idx) * kFlen + 10]);
+        put(lane, slot, f[(8 + idx) * kFlen + kSingleCol]);
     }
 }
 
@@ -59,7 +63,7 @@ template <int S>
 struct OctetCfg;
 // OTW x OTH own pixels per tile, one item of IW pixels per octet, NT threads.
 template <>
-struct OctetCfg<2> { static constexpr int OTW = 64, OTH = 32, IW = 32, NT = 512; };
+struct OctetCfg<2> { static constexpr int OTW = 64, OTH = 40, IW = 32, NT = 640; };
 template <>
 struct OctetCfg<3> { static constexpr int OTW = 64, OTH = 16, IW = 16, NT = 512; };
 template <>
@@ -93,11 +97,11 @@ struct OctetGeom {
     static_assert(ITEMS == NOCT && (S * C::OTH) % 4 == 0, "one item per octet and tile; tiles start on row quads");
 };
 
-template <int S>
+template <int S, int NBUF = 2>
 inline size_t octet_smem_bytes(int n_buckets)
 {
     using G = OctetGeom<S>;
-    return (size_t)n_buckets * kOctStride * sizeof(float) + 2 * (size_t)G::BUF_BYTES + 16;   // + two mbarriers
+    return (size_t)n_buckets * kOctStride * sizeof(float) + NBUF * (size_t)G::BUF_BYTES + 16;   // + two mbarriers
 }
 
 __device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gptr)
@@ -186,7 +190,10 @@ __device__ __forceinline__ void octet_issue_tile(const FilterParams& p, const CU
     }
 }
 
-template <int S, typename OutT>
+// NBUF = 2: the next tile is fetched while the current one is filtered.  NBUF = 1 (used when the
+// prep kernel of the next chunk shares the SM, see raisr_api.cu): one buffer, the fetch of the next
+// tile starts when the current one is done and the co-resident kernel fills the gap.
+template <int S, typename OutT, int NBUF = 2>
 __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const FilterParams p, const __grid_constant__ CUtensorMap tmap)
 {
     using C = OctetCfg<S>;
@@ -194,7 +201,7 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* tab = reinterpret_cast<float*>(smem_raw);                 // 512-byte records, 128-B aligned
     unsigned char* buf0 = smem_raw + (size_t)p.n_buckets * kOctStride * sizeof(float);
-    unsigned char* buf1 = buf0 + G::BUF_BYTES;
+    unsigned char* buf1 = buf0 + (NBUF - 1) * G::BUF_BYTES;
     const unsigned bar0 = (unsigned)__cvta_generic_to_shared(buf1 + G::BUF_BYTES), bar1 = bar0 + 8;
     const int tid = threadIdx.x;
     const int ntypes = S * S;
@@ -230,12 +237,12 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
     if (lane8 < 6) {
 #pragma unroll
         for (int t = 0; t < G::NEWP; ++t)
-            off_part[t] = (8 + lane8 / 2) + (5 * (lane8 % 2) + (5 - G::NEWP) + t) * G::PT;
+            off_part[t] = (8 + lane8 / 2) + (kRunCol0 + 5 * (lane8 % 2) + (5 - G::NEWP) + t) * G::PT;
     } else {
 #pragma unroll
         for (int t = 0; t < G::NEWP; ++t) {
-            int idx = (lane8 - 6) * G::NEWP + t;   // leftover taps (8,10) (9,10) (10,10)
-            off_part[t] = (idx < 3 ? (8 + idx) : 10) + 10 * G::PT;
+            int idx = (lane8 - 6) * G::NEWP + t;   // leftover taps (8,c) (9,c) (10,c), c = kSingleCol
+            off_part[t] = (idx < 3 ? (8 + idx) : 10) + kSingleCol * G::PT;
         }
     }
     const float4* tab_lane = reinterpret_cast<const float4*>(tab) + lane8;
@@ -245,13 +252,18 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
 
     int it = 0;
     for (int tile = worker; tile < ntiles; tile += nworkers, ++it) {
-        unsigned char* buf = (it & 1) ? buf1 : buf0;
+        unsigned char* buf = (NBUF == 2 && (it & 1)) ? buf1 : buf0;
         nxt.advance(nworkers, p.tiles_x, p.tiles_y);
-        if (tile + nworkers < ntiles && !(p.dbg_flags & 4))
-            octet_issue_tile<S>(p, &tmap, (it & 1) ? buf0 : buf1, (it & 1) ? bar0 : bar1, nxt, type, py, px);
-        cp_async_commit();
-        cp_async_wait<1>();   // hash bytes: everything but the newest group (the prefetch) has landed
-        mbar_wait((it & 1) ? bar1 : bar0, (it >> 1) & 1);   // U tile: TMA bytes have landed
+        if (NBUF == 2) {
+            if (tile + nworkers < ntiles && !(p.dbg_flags & 4))
+                octet_issue_tile<S>(p, &tmap, (it & 1) ? buf0 : buf1, (it & 1) ? bar0 : bar1, nxt, type, py, px);
+            cp_async_commit();
+            cp_async_wait<1>();   // hash bytes: everything but the newest group (the prefetch) has landed
+            mbar_wait((it & 1) ? bar1 : bar0, (it >> 1) & 1);   // U tile: TMA bytes have landed
+        } else {
+            cp_async_wait<0>();
+            mbar_wait(bar0, it & 1);
+        }
         __syncthreads();
 
         const int oy = cur.ty * C::OTH + row;
@@ -271,7 +283,7 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
 #pragma unroll
             for (int j = 0; j < kFlen; ++j) w11[j] = pf[j * G::PT];
             if (lane8 < 6) {
-                const float* pp = base + (8 + lane8 / 2) + 5 * (lane8 % 2) * G::PT;
+                const float* pp = base + (8 + lane8 / 2) + (kRunCol0 + 5 * (lane8 % 2)) * G::PT;
 #pragma unroll
                 for (int t = 0; t < 5 - G::NEWP; ++t) w5[t] = pp[t * G::PT];
             }
@@ -345,6 +357,10 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
         }
         cur = nxt;
         __syncthreads();   // tile consumed: its buffer may be refilled by the next prefetch
+        if (NBUF == 1) {
+            if (tile + nworkers < ntiles) octet_issue_tile<S>(p, &tmap, buf0, bar0, nxt, type, py, px);
+            cp_async_commit();
+        }
     }
     cp_async_wait<0>();
 }

@@ -82,7 +82,7 @@ def test_filter_record_packing_covers_every_tap_once():
                 put(p, j, p * 11 + j)
         for p in range(6):
             for t in range(5):
-                put(p, 11 + t, (8 + p // 2) * 11 + 5 * (p % 2) + t)
+                put(p, 11 + t, (8 + p // 2) * 11 + 1 + 5 * (p % 2) + t)
         for i in range(3):
-            put(6 + i // newp, 16 - newp + i % newp, (8 + i) * 11 + 10)
+            put(6 + i // newp, 16 - newp + i % newp, (8 + i) * 11 + 0)
         assert sorted(seen.values()) == list(range(121))

@@ -129,6 +129,29 @@ def test_batch_equals_single_frames(raisr):
     assert np.abs(np.rint(outf * 255) - out).max() <= 1
 
 
+def test_overlapped_pipeline_matches_serial(raisr):
+    # prep of chunk c+1 co-resident with the filter of chunk c (two streams, two scratch sets)
+    frames = synth.synthetic_batch(7, 200, 328, pool=7, seed=90)
+    serial = np.zeros((7, 400, 656), np.uint8)
+    raisr.set_option("chunk_budget_bytes", 2 << 20)
+    try:
+        raisr.upsample_batch(frames, serial, 2)
+        raisr.set_option("overlap", 1)
+        over = np.zeros_like(serial)
+        raisr.upsample_batch(frames, over, 2)
+        import torch
+        t_src = torch.from_numpy(frames).cuda()
+        t_dst = torch.zeros((7, 400, 656), dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        raisr.upsample_device(t_src.data_ptr(), 328, 200, 328, t_dst.data_ptr(), 656, 2, 7, np.uint8, timed=True)
+        dev = t_dst.cpu().numpy()
+    finally:
+        raisr.set_option("overlap", 0)
+        raisr.set_option("chunk_budget_bytes", 96 << 20)
+    assert np.array_equal(serial, over)
+    assert np.array_equal(serial, dev)
+
+
 def test_full_size_config2_frame(raisr):
     # BASELINE.json configs[1] frame size: 1080p -> 4K, compared in full against the C oracle
     src = synth.synthetic_frame(1080, 1920, 1000)
