@@ -30,8 +30,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SW, SH, SCALE, FRAMES = 1920, 1080, 2, 64       # BASELINE.json configs[1]
-FLOP_PER_PX = 412.0                             # SURVEY.md 8(d), minimal form
+FLOP_PER_PX = 412.0                             # SURVEY.md 8(d), minimal form: whole path
+FLOP_PER_PX_FILTER = 244.0                      # 121 FMA + store: the dominant kernel's share of the 412
 BYTES_PER_PX = 1.0 / (SCALE * SCALE) + 1.0      # u8 in -> u8 out
+# From the committed ncu capture of this command's kernels (profiles/r1g_ncu_summary.txt):
+NCU_FILTER_WAVEFRONTS_PER_PX = 4.83             # l1tex__data_pipe_lsu_wavefronts_mem_shared.sum / output pixels
+NCU_FILTER_DRAM_BYTES_PER_PX = 5.46             # dram__bytes_read.sum + dram__bytes_write.sum, per output pixel
 
 
 def make_inputs(n_frames, rank):
@@ -51,7 +55,7 @@ def cpu_baseline(budget_s=12.0):
     t0 = time.perf_counter()
     O.raisr_ref_c(frame, F, SCALE, nthreads=threads, want=("out_u8",))
     one = time.perf_counter() - t0
-    n = int(max(1, min(16, budget_s / max(one, 1e-3))))
+    n = int(max(1, min(64, budget_s / max(one, 1e-3))))
     t0 = time.perf_counter()
     for k in range(n):
         O.raisr_ref_c(frame, F, SCALE, nthreads=threads, want=("out_u8",))
@@ -121,7 +125,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES, help="frames per GPU per step")
@@ -237,13 +241,25 @@ def main():
         kern_s = (prep_ms + filt_ms) * 1e-3
         achieved_tf = FLOP_PER_PX * px_per_step * args.steps / kern_s / 1e12
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        clk_hz = info["sm_clock_khz"] * 1e3
+        filt_s = filt_ms * 1e-3
+        px_total = px_per_step * args.steps
+        chunk_frames = max(1, int((96 << 20) // (((dh + 18 + 3) // 4 * 4) * (dw + 10) * 4)))   # frames per kernel launch (scratch budget, as in raisr_api.cu)
         roofline = dict(bound="fp32_ffma", achieved=round(achieved_tf, 3), peak=round(peak_nominal, 2), unit="TFLOP/s",
-                        frac=round(achieved_tf / peak_nominal, 4), traffic=None,
+                        frac=round(achieved_tf / peak_nominal, 4),
+                        traffic=int(NCU_FILTER_DRAM_BYTES_PER_PX * chunk_frames * dw * dh),
+                        traffic_note="DRAM bytes per launch of the dominant kernel (ncu, profiles/); algorithmic %.0f" % (BYTES_PER_PX * chunk_frames * dw * dh),
                         peak_source="2*128*SMs*clocks.max.sm (SURVEY 8(d)); measured register-only FFMA kernel: %.1f TFLOP/s" % ffma_meas,
                         frac_of_measured_ffma=round(achieved_tf / ffma_meas, 4),
                         flop_per_px=FLOP_PER_PX,
                         kernels=dict(prep_ms_per_step=round(prep_ms / args.steps, 3), filter_ms_per_step=round(filt_ms / args.steps, 3),
                                      filter_share=round(filt_ms / (prep_ms + filt_ms), 3)),
+                        dominant_kernel=dict(
+                            name="filter_octet_kernel", flop_per_px=FLOP_PER_PX_FILTER,
+                            achieved_tflops=round(FLOP_PER_PX_FILTER * px_total / filt_s / 1e12, 3),
+                            binding_resource="shared-memory data pipe, 1 wavefront (128 B) per clock per SM: each pixel needs its own 484 B of fp32 taps",
+                            wavefronts_per_px=NCU_FILTER_WAVEFRONTS_PER_PX,
+                            smem_pipe_frac=round(NCU_FILTER_WAVEFRONTS_PER_PX * px_total / (filt_s * info["sm_count"] * clk_hz), 4)),
                         hbm=dict(algorithmic_bytes_per_px=BYTES_PER_PX,
                                  achieved_gbs=round(BYTES_PER_PX * px_per_step * args.steps / kern_s / 1e9, 1),
                                  peak_gbs=hbm_peak, peak_source="MEASURED_PEAKS.json" if peaks else "fallback 6650"))
