@@ -93,6 +93,15 @@ int raisr_bilinear_u8(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src
                       uint8_t* dst, int dw, int dh, size_t dst_pitch, int scale, int n_frames,
                       int where, float ms[3]);
 
+/* Stand-alone interpolation, SURVEY.md 8(f) row N2: replaces clUtility.bilinear / bilinear_lds / bicubic /
+ * bicubic_lds (basic/interpolation.py:37-107, kernels basic/interpolation.cl:3-211).  Interleaved u8
+ * image with 1 or 4 channels (the reference uses BGRA), any output size >= 2x2.
+ * mode: 0 = bilinear_lds (align-corners), 1 = bicubic / bicubic_lds (Catmull-Rom), 2 = bilinear (the
+ * normalised-coordinate CLK_FILTER_LINEAR sampler of bilinear_simple). */
+int raisr_resize_u8(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_pitch, int channels,
+                    uint8_t* dst, int dw, int dh, size_t dst_pitch, int mode, int n_frames, int where,
+                    float ms[3]);
+
 /* Parity probe: the per-pixel quantities of raisr.cl:278-317 for one frame.  All outputs are
  * dense dh x dw arrays in `where` memory, any may be NULL: hash (int32, full index into the
  * filter table incl. pixel type), angle (theta in [0,pi)), l1 (strength), coherence, and the

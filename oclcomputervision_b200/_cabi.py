@@ -30,6 +30,8 @@ SIGNATURES = {
                                    c_size_t, c_int, c_int, c_int, POINTER(c_float)]),
     "raisr_bilinear_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_void_p, c_int, c_int,
                                   c_size_t, c_int, c_int, c_int, POINTER(c_float)]),
+    "raisr_resize_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_void_p, c_int, c_int, c_size_t,
+                                c_int, c_int, c_int, POINTER(c_float)]),
     "raisr_debug_hash": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_int]),
     "raisr_upsample_band_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_int, c_void_p,

@@ -21,6 +21,7 @@
 #include "raisr_filter.cuh"
 #include "raisr_octet.cuh"
 #include "raisr_prep.cuh"
+#include "raisr_resize.cuh"
 
 using namespace raisr;
 
@@ -672,6 +673,55 @@ int raisr_bilinear_u8(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src
     BilinearParams bp{dsrc, src_pitch, src_frame, ddst, dst_pitch, dst_frame, sw, sh, dw, dh};
     dim3 grid(((dw + 3) / 4 + 255) / 256, dh, n_frames);
     bilinear_u8_kernel<<<grid, 256, 0, st>>>(bp);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    cudaEventRecord(h->ev(2), st);
+    if (where == RAISR_HOST) {
+        CUDA_TRY(cudaMemcpyAsync(dst, ddst, dst_frame * n_frames, cudaMemcpyDeviceToHost, st));
+        cudaEventRecord(h->ev(3), st);
+    }
+    if (where == RAISR_HOST || ms) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (ms) {
+            ms[0] = ms[2] = 0;
+            cudaEventElapsedTime(&ms[1], h->ev(1), h->ev(2));
+            if (where == RAISR_HOST) {
+                cudaEventElapsedTime(&ms[0], h->ev(0), h->ev(1));
+                cudaEventElapsedTime(&ms[2], h->ev(2), h->ev(3));
+            }
+        }
+    }
+    return 0;
+}
+
+int raisr_resize_u8(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_pitch, int channels, uint8_t* dst, int dw,
+                    int dh, size_t dst_pitch, int mode, int n_frames, int where, float ms[3])
+{
+    if (!h) return fail(RAISR_E_ARG, "null handle");
+    if (!src || !dst) return fail(RAISR_E_ARG, "null image pointer");
+    if (channels != 1 && channels != 4) return fail(RAISR_E_ARG, "channels must be 1 or 4 (got %d)", channels);
+    if (mode < 0 || mode > 2) return fail(RAISR_E_ARG, "mode must be 0 (bilinear_lds), 1 (bicubic) or 2 (bilinear)");
+    if (sw < 1 || sh < 1 || dw < 2 || dh < 2 || n_frames < 1) return fail(RAISR_E_ARG, "bad shapes: src %dx%d dst %dx%d", sw, sh, dw, dh);
+    if (src_pitch < (size_t)sw * channels || dst_pitch < (size_t)dw * channels) return fail(RAISR_E_ARG, "pitch smaller than a row");
+    if (channels == 4 && where == RAISR_DEVICE && (((uintptr_t)dst | dst_pitch) & 3)) return fail(RAISR_E_ARG, "4-channel dst must be 4-byte aligned");
+    Guard guard(h->device);
+    cudaStream_t st = h->stream();
+    const size_t src_frame = src_pitch * sh, dst_frame = dst_pitch * dh;
+    const uint8_t* dsrc = src;
+    uint8_t* ddst = dst;
+    if (where == RAISR_HOST) {
+        if (dst_pitch & 3) return fail(RAISR_E_ARG, "dst pitch must be a multiple of 4 bytes");
+        if (int rc = h->dsrc[0].ensure(src_frame * n_frames)) return rc;
+        if (int rc = h->ddst[0].ensure(dst_frame * n_frames)) return rc;
+        dsrc = (const uint8_t*)h->dsrc[0].p; ddst = (uint8_t*)h->ddst[0].p;
+        cudaEventRecord(h->ev(0), st);
+        CUDA_TRY(cudaMemcpyAsync(h->dsrc[0].p, src, src_frame * n_frames, cudaMemcpyHostToDevice, st));
+    }
+    cudaEventRecord(h->ev(1), st);
+    ResizeParams rp{dsrc, src_pitch, src_frame, ddst, dst_pitch, dst_frame, sw, sh, dw, dh, channels, mode};
+    dim3 grid((dw + 255) / 256, dh, n_frames);
+    if (channels == 4) resize_kernel<4><<<grid, 256, 0, st>>>(rp);
+    else resize_kernel<1><<<grid, 256, 0, st>>>(rp);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     cudaEventRecord(h->ev(2), st);

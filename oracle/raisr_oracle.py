@@ -236,6 +236,9 @@ def _load():
         lib.raisr_oracle_bilinear_u8.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t,
                                                  ctypes.c_int, vp]
         lib.raisr_oracle_max_threads.restype = ctypes.c_int
+        lib.raisr_oracle_resize_u8.restype = ctypes.c_int
+        lib.raisr_oracle_resize_u8.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_int, vp,
+                                               ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_int]
         _lib = lib
     return _lib
 
@@ -292,4 +295,21 @@ def bilinear_u8_c(src_u8: np.ndarray, s: int) -> np.ndarray:
                                       dst.ctypes.data)
     if rc != 0:
         raise RuntimeError("raisr_oracle_bilinear_u8 failed")
+    return dst
+
+
+RESIZE_MODES = {"bilinear_lds": 0, "bicubic": 1, "bicubic_lds": 1, "bilinear": 2}
+
+
+def resize_u8_c(src: np.ndarray, out_hw, mode: str) -> np.ndarray:
+    """C restatement of basic/interpolation.cl (see raisr_oracle.c: raisr_oracle_resize_u8)."""
+    lib = _load()
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    ch = 1 if src.ndim == 2 else src.shape[2]
+    dh, dw = out_hw
+    dst = np.empty((dh, dw) if src.ndim == 2 else (dh, dw, ch), np.uint8)
+    rc = lib.raisr_oracle_resize_u8(src.ctypes.data, src.shape[1], src.shape[0], src.strides[0], ch, dst.ctypes.data,
+                                    dw, dh, dst.strides[0], RESIZE_MODES[mode])
+    if rc != 0:
+        raise RuntimeError("raisr_oracle_resize_u8 failed")
     return dst
