@@ -86,6 +86,18 @@ int raisr_upsample_f32(raisr_t* h, const uint8_t* src, int sw, int sh, size_t sr
                        float* dst, int dw, int dh, size_t dst_pitch, int scale, int n_frames,
                        int where, float ms[3]);
 
+/* Colour form of ClRaisr.upsample, i.e. grayMode == 0 (raisr.py:101-104), the mode the reference's own
+ * __main__ runs (raisr.py:139,163-164): interleaved 8-bit BGRA in and out (pitches in bytes, multiples
+ * of 4).  RGB->YUV (raisr.py:20-25, raisr.cl:211-214), hash from Y, the hashed filter on all four planes
+ * (raisr.cl:322-330), YUV->RGB (raisr.py:26-31, raisr.cl:333-336), saturating store.  The _f32 variant
+ * writes the four clamped float components per pixel (memory order B,G,R,A) for the 1e-4 parity check. */
+int raisr_upsample_bgra_u8(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_pitch,
+                           uint8_t* dst, int dw, int dh, size_t dst_pitch, int scale, int n_frames,
+                           int where, float ms[3]);
+int raisr_upsample_bgra_f32(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_pitch,
+                            float* dst, int dw, int dh, size_t dst_pitch, int scale, int n_frames,
+                            int where, float ms[3]);
+
 /* What the SHIPPED kernel computes (it returns after the cheap upscale, raisr.cl:219-230) and
  * what basic/interpolation.cl:17-71 (bilinear_lds) computes for one channel: align-corners
  * bilinear, u8 -> u8.  No filter table needed. */

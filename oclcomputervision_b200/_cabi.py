@@ -28,6 +28,10 @@ SIGNATURES = {
                                   c_size_t, c_int, c_int, c_int, POINTER(c_float)]),
     "raisr_upsample_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_void_p, c_int, c_int,
                                    c_size_t, c_int, c_int, c_int, POINTER(c_float)]),
+    "raisr_upsample_bgra_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_void_p, c_int, c_int,
+                                       c_size_t, c_int, c_int, c_int, POINTER(c_float)]),
+    "raisr_upsample_bgra_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_void_p, c_int, c_int,
+                                        c_size_t, c_int, c_int, c_int, POINTER(c_float)]),
     "raisr_bilinear_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_void_p, c_int, c_int,
                                   c_size_t, c_int, c_int, c_int, POINTER(c_float)]),
     "raisr_resize_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_void_p, c_int, c_int, c_size_t,

@@ -20,6 +20,7 @@
 
 #include "raisr_filter.cuh"
 #include "raisr_octet.cuh"
+#include "raisr_color.cuh"
 #include "raisr_prep.cuh"
 #include "raisr_resize.cuh"
 
@@ -92,6 +93,7 @@ struct raisr_ctx {
     ScaleTable tables[5];  // index = scale (2..4)
     DevBuf uext, hash, dsrc[2], ddst[2], dbg;
     DevBuf uext2, hash2;          // second scratch set of the overlapped pipeline
+    DevBuf cplanes;               // colour path: four filtered float planes
     cudaStream_t prep_stream = nullptr, filt_stream = nullptr;
     int overlap = 0;              // 1: prep of chunk c+1 shares the SMs with the filter of chunk c
     std::vector<cudaEvent_t> ev_pool;
@@ -156,7 +158,7 @@ Geometry make_geometry(int sw, int rows_out, int s)
     return g;
 }
 
-template <int S, bool DBG, int NQ>
+template <int S, bool DBG, int NQ, bool FROM_U>
 void launch_prep_q(PrepParams p, cudaStream_t st, int max_ctas)
 {
     p.tiles_x = (p.dw + PT_W - 1) / PT_W;
@@ -164,16 +166,20 @@ void launch_prep_q(PrepParams p, cudaStream_t st, int max_ctas)
     long long total = (long long)p.tiles_x * p.tiles_y * p.n_frames;
     int grid = (int)std::max<long long>(1, std::min<long long>(total, max_ctas));
     size_t smem = sizeof(PrepSmem);
-    cudaFuncSetAttribute(prep_kernel<S, DBG, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    prep_kernel<S, DBG, NQ><<<grid, PT_THREADS, smem, st>>>(p);
+    cudaFuncSetAttribute(prep_kernel<S, DBG, NQ, FROM_U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    prep_kernel<S, DBG, NQ, FROM_U><<<grid, PT_THREADS, smem, st>>>(p);
 }
 
 template <int S>
 void launch_prep_t(const PrepParams& p, cudaStream_t st, bool dbg, int max_ctas)
 {
     const bool small = p.n_strength <= 3 && p.n_coherence <= 3;   // the reference's 3 x 3 (raisr.cl:9-15)
-    if (dbg) small ? launch_prep_q<S, true, 2>(p, st, max_ctas) : launch_prep_q<S, true, kMaxQ>(p, st, max_ctas);
-    else small ? launch_prep_q<S, false, 2>(p, st, max_ctas) : launch_prep_q<S, false, kMaxQ>(p, st, max_ctas);
+    if (p.uext_in) {   // colour path: hash an existing upscaled plane
+        small ? launch_prep_q<S, false, 2, true>(p, st, max_ctas) : launch_prep_q<S, false, kMaxQ, true>(p, st, max_ctas);
+        return;
+    }
+    if (dbg) small ? launch_prep_q<S, true, 2, false>(p, st, max_ctas) : launch_prep_q<S, true, kMaxQ, false>(p, st, max_ctas);
+    else small ? launch_prep_q<S, false, 2, false>(p, st, max_ctas) : launch_prep_q<S, false, kMaxQ, false>(p, st, max_ctas);
 }
 
 // ctas_per_sm == 0: one CTA per tile (the hardware scheduler balances); > 0: persistent grid of that many CTAs per SM
@@ -571,7 +577,7 @@ void raisr_destroy(raisr_t* h)
     Guard guard(h->device);
     cudaDeviceSynchronize();
     for (auto& t : h->tables) { t.block.release(); t.octet.release(); }
-    h->uext.release(); h->hash.release(); h->dbg.release(); h->uext2.release(); h->hash2.release();
+    h->uext.release(); h->hash.release(); h->dbg.release(); h->uext2.release(); h->hash2.release(); h->cplanes.release();
     if (h->prep_stream) cudaStreamDestroy(h->prep_stream);
     if (h->filt_stream) cudaStreamDestroy(h->filt_stream);
     for (int b = 0; b < 2; ++b) { h->dsrc[b].release(); h->ddst[b].release(); }
@@ -692,6 +698,102 @@ int raisr_bilinear_u8(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src
         }
     }
     return 0;
+}
+
+static int upsample_bgra_impl(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_pitch, uint8_t* dst_u8, float* dst_f32, int dw,
+                              int dh, size_t dst_pitch, int scale, int n_frames, int where, float ms[3])
+{
+    const bool f32 = dst_f32 != nullptr;
+    const void* dst = f32 ? (const void*)dst_f32 : (const void*)dst_u8;
+    if (!h) return fail(RAISR_E_ARG, "null handle");
+    if (!src || !dst) return fail(RAISR_E_ARG, "null image pointer");
+    if (sw < 1 || sh < 1 || n_frames < 1) return fail(RAISR_E_ARG, "bad source shape %dx%d x%d", sw, sh, n_frames);
+    if (src_pitch < (size_t)sw * 4 || dst_pitch < (size_t)dw * 4 * (f32 ? 4 : 1)) return fail(RAISR_E_ARG, "pitch smaller than a row");
+    if (scale < 2 || scale > 4 || !h->tables[scale].set) return fail(RAISR_E_UNSUPPORTED, "not trained for scale factor %d", scale);
+    if (dw != sw * scale || dh != sh * scale) return fail(RAISR_E_ARG, "dst shape %dx%d is not %d x src shape %dx%d", dw, dh, scale, sw, sh);
+    if ((src_pitch & 3) || (dst_pitch & 3)) return fail(RAISR_E_ARG, "BGRA pitches must be multiples of 4 bytes");
+    if (h->filter_impl != 1) return fail(RAISR_E_UNSUPPORTED, "the colour path needs the octet filter kernel");
+    Guard guard(h->device);
+    cudaStream_t st = h->stream();
+    Geometry g = make_geometry(sw, dh, scale);
+    const size_t src_frame = src_pitch * sh, dst_frame = dst_pitch * dh;
+    const size_t fpitch = round_up((size_t)dw, 4), fplane = fpitch * dh;
+    if (int rc = h->uext.ensure(g.uext_frame * sizeof(float) * 4)) return rc;
+    if (int rc = h->hash.ensure(g.hash_frame)) return rc;
+    if (int rc = h->cplanes.ensure(fplane * sizeof(float) * 4)) return rc;
+    const uint8_t* dsrc = src;
+    unsigned char* ddst = (unsigned char*)dst;
+    if (where == RAISR_HOST) {
+        if (int rc = h->dsrc[0].ensure(src_frame * n_frames)) return rc;
+        if (int rc = h->ddst[0].ensure(dst_frame * n_frames)) return rc;
+        dsrc = (const uint8_t*)h->dsrc[0].p; ddst = (unsigned char*)h->ddst[0].p;
+        cudaEventRecord(h->ev(0), st);
+        CUDA_TRY(cudaMemcpyAsync(h->dsrc[0].p, src, src_frame * n_frames, cudaMemcpyHostToDevice, st));
+    } else if (where != RAISR_DEVICE) {
+        return fail(RAISR_E_ARG, "where must be RAISR_HOST or RAISR_DEVICE");
+    }
+    cudaEventRecord(h->ev(1), st);
+    for (int f = 0; f < n_frames; ++f) {
+        ColorUpParams cu{};
+        cu.src = dsrc + (size_t)f * src_frame; cu.src_pitch = src_pitch;
+        cu.sw = sw; cu.sh = sh; cu.dw = dw; cu.dh = dh; cu.pitch = g.uext_pitch;
+        for (int k = 0; k < 4; ++k) cu.plane[k] = (float*)h->uext.p + g.uext_frame * k;
+        dim3 gu((dw + 2 * kMargin + 255) / 256, (dh + 2 * kMargin + 3) / 4);
+        color_upscale_kernel<<<gu, 256, 0, st>>>(cu);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+        PrepParams pp;
+        FilterParams fp;
+        fill_params(h, g, dsrc, sw, sh, src_pitch, h->cplanes.p, fpitch * sizeof(float), scale, 0, 1, (float*)h->uext.p, (uint8_t*)h->hash.p, pp, fp);
+        pp.uext_in = (const float*)h->uext.p;   // Y plane
+        if (int rc = launch_prep(h, pp, scale, st, false)) return rc;
+        for (int k = 0; k < 4; ++k) {
+            fp.uext = (const float*)h->uext.p + g.uext_frame * k;
+            fp.dst = (float*)h->cplanes.p + fplane * k;
+            fp.raw_f32 = 1;
+            if (int rc = launch_filter<float>(h, fp, scale, st)) return rc;
+        }
+        ColorPackParams cp{};
+        for (int k = 0; k < 4; ++k) cp.plane[k] = (const float*)h->cplanes.p + fplane * k;
+        cp.pitch = fpitch; cp.dw = dw; cp.dh = dh;
+        if (f32) { cp.dst_f32 = (float*)(ddst + (size_t)f * dst_frame); cp.dst_f32_pitch = dst_pitch / 4; }
+        else { cp.dst = ddst + (size_t)f * dst_frame; cp.dst_pitch = dst_pitch; }
+        dim3 gp((dw + 255) / 256, dh);
+        color_pack_kernel<<<gp, 256, 0, st>>>(cp);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    cudaEventRecord(h->ev(2), st);
+    if (where == RAISR_HOST) {
+        CUDA_TRY(cudaMemcpyAsync((void*)dst, ddst, dst_frame * n_frames, cudaMemcpyDeviceToHost, st));
+        cudaEventRecord(h->ev(3), st);
+    }
+    if (where == RAISR_HOST || ms) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (ms) {
+            ms[0] = ms[2] = 0;
+            cudaEventElapsedTime(&ms[1], h->ev(1), h->ev(2));
+            if (where == RAISR_HOST) {
+                cudaEventElapsedTime(&ms[0], h->ev(0), h->ev(1));
+                cudaEventElapsedTime(&ms[2], h->ev(2), h->ev(3));
+            }
+        }
+    }
+    return 0;
+}
+
+int raisr_upsample_bgra_u8(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_pitch, uint8_t* dst, int dw, int dh,
+                           size_t dst_pitch, int scale, int n_frames, int where, float ms[3])
+{
+    if (!dst) return fail(RAISR_E_ARG, "null image pointer");
+    return upsample_bgra_impl(h, src, sw, sh, src_pitch, dst, nullptr, dw, dh, dst_pitch, scale, n_frames, where, ms);
+}
+
+int raisr_upsample_bgra_f32(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_pitch, float* dst, int dw, int dh,
+                            size_t dst_pitch, int scale, int n_frames, int where, float ms[3])
+{
+    if (!dst) return fail(RAISR_E_ARG, "null image pointer");
+    return upsample_bgra_impl(h, src, sw, sh, src_pitch, nullptr, dst, dw, dh, dst_pitch, scale, n_frames, where, ms);
 }
 
 int raisr_resize_u8(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_pitch, int channels, uint8_t* dst, int dw,

@@ -37,6 +37,7 @@ struct FilterParams {
     int n_frames;
     int tiles_x, tiles_y;
     int dbg_flags;            // timing experiments only (results become wrong when non-zero)
+    int raw_f32;              // float output is stored unclamped (colour path: CSC back happens before saturation)
 };
 
 template <int S, int OTW, int OTH, int BR, int BC>

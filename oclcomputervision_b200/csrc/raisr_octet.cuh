@@ -352,7 +352,10 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
                 float keep = h0 ? r2[1] : r2[0];
                 float v = keep + __shfl_xor_sync(omask, send, 1);
                 const int ox = oxs + b0 + lane8;
-                if (ox < p.ow && !(p.dbg_flags & 2)) store_px(drow + (S * ox + px), v);
+                if (ox < p.ow && !(p.dbg_flags & 2)) {
+                    if (sizeof(OutT) == 4 && p.raw_f32) *reinterpret_cast<float*>(drow + (S * ox + px)) = v;
+                    else store_px(drow + (S * ox + px), v);
+                }
             }
         }
         cur = nxt;

@@ -13,7 +13,8 @@ Buffer plumbing (raisr.py:62-77,96-133) is replaced by one handle of the C-ABI l
 * the intended hash semantics of SURVEY.md 8(a) are computed -- the shipped OpenCL kernel returns
   after the bilinear stage (raisr.cl:219-230); ``bilinear_only`` reproduces exactly that.
 
-Only the gray path (``grayMode == 1``, raisr.py:97-100) is built so far.
+Both modes of the reference are built: gray (``grayMode == 1``, raisr.py:97-100, the contract path of
+the benchmark) and BGRA colour (``grayMode == 0``, raisr.py:101-104, what its ``__main__`` runs).
 """
 from __future__ import annotations
 
@@ -56,9 +57,8 @@ class ClRaisr:
     def __init__(self, grayMode, filters: Optional[np.ndarray] = None, device: int = 0,
                  n_angle: int = 24, n_strength: int = 3, n_coherence: int = 3,
                  filter_path: Optional[str] = None):
-        if grayMode != 1:
-            raise NotImplementedError(
-                "only the gray path (grayMode=1, raisr.py:97-100) is built; the BGRA path is row N1 of SURVEY.md 8(f)")
+        if grayMode not in (0, 1):
+            raise ValueError("grayMode must be 1 (gray, raisr.py:97-100) or 0 (BGRA, raisr.py:101-104)")
         self.grayMode = grayMode
         self.n_angle, self.n_strength, self.n_coherence = n_angle, n_strength, n_coherence
         self._lib = _cabi.load()
@@ -105,8 +105,15 @@ class ClRaisr:
             # reference behaviour for an untrained scale (raisr.py:93-94)
             print('Fatal. not trained for scale factor {}'.format(scale_factor))
             return
-        src, dst = self._check_pair(src, dst, np.uint8)
         ms = (ctypes.c_float * 3)()
+        if self.grayMode == 0:   # BGRA images (raisr.py:101-104,163-164)
+            src, dst = self._check_pair(src, dst, np.uint8, channels=4)
+            _cabi.check(self._lib.raisr_upsample_bgra_u8(
+                self._h, src.ctypes.data, src.shape[1], src.shape[0], src.strides[0],
+                dst.ctypes.data, dst.shape[1], dst.shape[0], dst.strides[0],
+                int(scale_factor), 1, _cabi.RAISR_HOST, ms))
+            return get_elapsed_ms(ms)
+        src, dst = self._check_pair(src, dst, np.uint8)
         _cabi.check(self._lib.raisr_upsample_u8(
             self._h, src.ctypes.data, src.shape[1], src.shape[0], src.strides[0],
             dst.ctypes.data, dst.shape[1], dst.shape[0], dst.strides[0],
@@ -136,9 +143,15 @@ class ClRaisr:
     def upsample_f32(self, src, scale_factor) -> np.ndarray:
         """Float [0,1] output of one frame (the value the reference's write_imagef would quantise)."""
         src = np.ascontiguousarray(src, dtype=np.uint8)
-        dst = np.empty((src.shape[0] * scale_factor, src.shape[1] * scale_factor), np.float32)
         if scale_factor not in self._filters:
             raise ValueError("not trained for scale factor %d" % scale_factor)
+        if self.grayMode == 0:
+            dst = np.empty((src.shape[0] * scale_factor, src.shape[1] * scale_factor, 4), np.float32)
+            _cabi.check(self._lib.raisr_upsample_bgra_f32(self._h, src.ctypes.data, src.shape[1], src.shape[0], src.strides[0],
+                                                          dst.ctypes.data, dst.shape[1], dst.shape[0], dst.strides[0],
+                                                          int(scale_factor), 1, _cabi.RAISR_HOST, None))
+            return dst
+        dst = np.empty((src.shape[0] * scale_factor, src.shape[1] * scale_factor), np.float32)
         _cabi.check(self._lib.raisr_upsample_f32(self._h, src.ctypes.data, src.shape[1], src.shape[0], src.strides[0],
                                                  dst.ctypes.data, dst.shape[1], dst.shape[0], dst.strides[0],
                                                  int(scale_factor), 1, _cabi.RAISR_HOST, None))
@@ -199,14 +212,17 @@ class ClRaisr:
         return t.value
 
     @staticmethod
-    def _check_pair(src, dst, dtype):
+    def _check_pair(src, dst, dtype, channels=1):
         if not isinstance(src, np.ndarray) or not isinstance(dst, np.ndarray):
             raise TypeError("src and dst must be numpy arrays")
-        if src.ndim != 2 or dst.ndim != 2:
-            raise ValueError("gray mode expects 2-D arrays (raisr.py:98)")
+        if channels == 1:
+            if src.ndim != 2 or dst.ndim != 2:
+                raise ValueError("gray mode expects 2-D arrays (raisr.py:98)")
+        elif src.ndim != 3 or dst.ndim != 3 or src.shape[2] != channels or dst.shape[2] != channels:
+            raise ValueError("colour mode expects (h, w, 4) BGRA arrays (raisr.py:102,163-164)")
         if src.dtype != dtype or dst.dtype != dtype:
             raise ValueError("src and dst must be %s" % np.dtype(dtype).name)
-        if src.strides[1] != 1 or dst.strides[1] != 1:
+        if src.strides[-1] != 1 or dst.strides[-1] != 1 or (channels > 1 and (src.strides[1] != channels or dst.strides[1] != channels)):
             raise ValueError("rows must be contiguous")
         return src, dst
 

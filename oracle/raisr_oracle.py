@@ -236,6 +236,9 @@ def _load():
         lib.raisr_oracle_bilinear_u8.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t,
                                                  ctypes.c_int, vp]
         lib.raisr_oracle_max_threads.restype = ctypes.c_int
+        lib.raisr_oracle_run_bgra.restype = ctypes.c_int
+        lib.raisr_oracle_run_bgra.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_int, vp, ctypes.c_int,
+                                              ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int]
         lib.raisr_oracle_resize_u8.restype = ctypes.c_int
         lib.raisr_oracle_resize_u8.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_int, vp,
                                                ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_int]
@@ -313,3 +316,23 @@ def resize_u8_c(src: np.ndarray, out_hw, mode: str) -> np.ndarray:
     if rc != 0:
         raise RuntimeError("raisr_oracle_resize_u8 failed")
     return dst
+
+
+def raisr_ref_bgra_c(src_bgra: np.ndarray, filters: np.ndarray, s: int = 2, *, n_angle=24, n_strength=3, n_coherence=3,
+                     strength_q=DEFAULT_STRENGTH_Q, coherence_q=DEFAULT_COHERENCE_Q, nthreads: int = 0) -> Dict[str, np.ndarray]:
+    """C restatement of the colour (BGRA) path (raisr_oracle.c: raisr_oracle_run_bgra)."""
+    lib = _load()
+    src = np.ascontiguousarray(src_bgra, dtype=np.uint8)
+    assert src.ndim == 3 and src.shape[2] == 4
+    sh, sw = src.shape[:2]
+    dh, dw = sh * s, sw * s
+    flt = np.ascontiguousarray(filters, dtype=F32)
+    sq = np.ascontiguousarray(strength_q, dtype=F32)
+    cq = np.ascontiguousarray(coherence_q, dtype=F32)
+    res = dict(hash=np.empty((dh, dw), np.int32), out_f32=np.empty((dh, dw, 4), F32), out_u8=np.empty((dh, dw, 4), np.uint8))
+    rc = lib.raisr_oracle_run_bgra(src.ctypes.data, sw, sh, src.strides[0], s, flt.ctypes.data, n_angle, n_strength, n_coherence,
+                                   sq.ctypes.data, cq.ctypes.data, res["hash"].ctypes.data, res["out_f32"].ctypes.data,
+                                   res["out_u8"].ctypes.data, int(nthreads))
+    if rc != 0:
+        raise RuntimeError("raisr_oracle_run_bgra failed (%d)" % rc)
+    return res

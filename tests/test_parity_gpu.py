@@ -199,5 +199,29 @@ def test_error_behaviour(raisr):
         raisr.upsample(src.astype(np.float32), np.zeros((16, 16), np.uint8), 2)
     with pytest.raises(ValueError):
         raisr.filters_x2 = np.zeros((24, 3, 3, 4, 120), np.float32)
-    with pytest.raises(NotImplementedError):
-        ClRaisr(0)
+    with pytest.raises(ValueError):
+        ClRaisr(2)
+
+
+@pytest.mark.parametrize("shape,s", [((40, 56), 2), ((37, 53), 2), ((24, 32), 3), ((96, 130), 2)])
+def test_colour_bgra_path_against_oracle(shape, s):
+    # grayMode = 0 is what the reference's __main__ runs (raisr.py:139,163-164)
+    rng = np.random.default_rng(shape[1])
+    planes = [synth.synthetic_frame(shape[0], shape[1], 300 + k, sigma=2.0) for k in range(3)]
+    alpha = rng.integers(200, 256, shape, dtype=np.uint8)
+    src = np.stack(planes + [alpha], axis=2).copy()
+    F = synth.random_filters(s)
+    r = ClRaisr(0)
+    setattr(r, "filters_x%d" % s, F)
+    ref = O.raisr_ref_bgra_c(src, F, s)
+    out = r.upsample_f32(src, s)
+    dst = np.zeros((shape[0] * s, shape[1] * s, 4), np.uint8)
+    ms = r.upsample(src, dst, s)
+    assert len(ms) == 3
+    err = np.abs(out - ref["out_f32"]).max(axis=2)
+    bad = err >= TOL_F32
+    # a pixel whose hash sits on a bin edge may legitimately use a neighbouring filter: count, bound
+    print("colour: max err %.3g, pixels over tolerance %d of %d" % (err[~bad].max(), int(bad.sum()), bad.size))
+    assert bad.mean() < 2e-4
+    assert (np.abs(dst.astype(int) - ref["out_u8"].astype(int)).max(axis=2)[~bad] <= 1).all()
+    r.close()
