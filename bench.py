@@ -131,8 +131,8 @@ def main():
     ap.add_argument("--frames", type=int, default=FRAMES, help="frames per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--filter-impl", type=int, default=None, help="1 octet (default), 0 block")
-    ap.add_argument("--dbg-flags", type=int, default=0, help="kernel timing experiments (results invalid)")
     ap.add_argument("--overlap", type=int, default=None, help="1: overlapped prep/filter pipeline, 0: serial")
+    ap.add_argument("--chunk-mb", type=int, default=208, help="scratch budget per kernel launch in MiB (library default 208)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -155,10 +155,10 @@ def main():
     r = ClRaisr(1, filters=F, device=local_rank)
     if args.filter_impl is not None:
         r.set_option("filter_impl", args.filter_impl)
-    if args.dbg_flags:
-        r.set_option("dbg_flags", args.dbg_flags)
     if args.overlap is not None:
         r.set_option("overlap", args.overlap)
+    if args.chunk_mb is not None:
+        r.set_option("chunk_budget_bytes", args.chunk_mb << 20)
     info = r.device_info()
     n = args.frames
     dw, dh = SW * SCALE, SH * SCALE
@@ -244,7 +244,7 @@ def main():
         clk_hz = info["sm_clock_khz"] * 1e3
         filt_s = filt_ms * 1e-3
         px_total = px_per_step * args.steps
-        chunk_frames = max(1, int((96 << 20) // (((dh + 18 + 3) // 4 * 4) * (dw + 10) * 4)))   # frames per kernel launch (scratch budget, as in raisr_api.cu)
+        chunk_frames = max(1, min(n, int((args.chunk_mb << 20) // (((dh + 18 + 3) // 4 * 4) * (dw + 10) * 4))))   # frames per kernel launch (as in raisr_api.cu)
         roofline = dict(bound="fp32_ffma", achieved=round(achieved_tf, 3), peak=round(peak_nominal, 2), unit="TFLOP/s",
                         frac=round(achieved_tf / peak_nominal, 4),
                         traffic=int(NCU_FILTER_DRAM_BYTES_PER_PX * chunk_frames * dw * dh),

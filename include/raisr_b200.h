@@ -65,7 +65,9 @@ int raisr_set_quantizers(raisr_t* h, const float* strength_q, int n_sq, const fl
 int raisr_set_stream(raisr_t* h, void* cuda_stream);
 
 /* Tuning knobs without a reference counterpart.  Keys: "filter_impl" (1 = octet kernel, default;
- * 0 = block kernel), "chunk_budget_bytes" (size of the per-chunk upscaled-image scratch). */
+ * 0 = block kernel), "chunk_budget_bytes" (size of the per-launch upscaled-image scratch, default 208 MiB),
+ * "overlap" (1 = experimental two-stream pipeline that co-schedules the prep kernel of the next chunk
+ * with the filter kernel of the current one; default 0, slower on B200). */
 int raisr_set_option(raisr_t* h, const char* key, long long value);
 
 /* Replaces ClRaisr.upsample (raisr.py:85-135) for gray frames: H2D copy, the fused RAISR kernels

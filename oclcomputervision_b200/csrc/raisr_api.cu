@@ -100,8 +100,7 @@ struct raisr_ctx {
     long long launches = 0;
     float last_prep_ms = 0, last_filter_ms = 0;
     int filter_impl = 1;  // 0 = block (v1), 1 = octet
-    int dbg_flags = 0;
-    size_t chunk_budget = 96u << 20;
+    size_t chunk_budget = 208u << 20;   // upscaled-image scratch per kernel launch: 6 frames of 1080p->4K
 
     cudaStream_t stream() const { return use_user_stream ? user_stream : own_stream; }
     cudaEvent_t ev(size_t i)
@@ -272,7 +271,6 @@ template <typename OutT>
 int launch_filter(raisr_ctx* h, FilterParams p, int s, cudaStream_t st, bool single_buffer = false)
 {
     ScaleTable& t = h->tables[s];
-    p.dbg_flags = h->dbg_flags;
     if (h->filter_impl == 1) {
         p.table = (const float*)t.octet.p;
         if (single_buffer) {
@@ -637,7 +635,6 @@ int raisr_set_option(raisr_t* h, const char* key, long long value)
 {
     if (!h || !key) return fail(RAISR_E_ARG, "null argument");
     if (!strcmp(key, "filter_impl")) { h->filter_impl = value ? 1 : 0; return 0; }
-    if (!strcmp(key, "dbg_flags")) { h->dbg_flags = (int)value; return 0; }
     if (!strcmp(key, "overlap")) { h->overlap = value ? 1 : 0; return 0; }
     if (!strcmp(key, "chunk_budget_bytes")) { h->chunk_budget = (size_t)std::max<long long>(value, 1 << 20); return 0; }
     return fail(RAISR_E_ARG, "unknown option %s", key);

@@ -36,7 +36,6 @@ struct FilterParams {
     int ow, oh;               // own columns (= source width) / own rows of this launch (= rows / S)
     int n_frames;
     int tiles_x, tiles_y;
-    int dbg_flags;            // timing experiments only (results become wrong when non-zero)
     int raw_f32;              // float output is stored unclamped (colour path: CSC back happens before saturation)
 };
 

@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
         unsigned char* buf = (NBUF == 2 && (it & 1)) ? buf1 : buf0;
         nxt.advance(nworkers, p.tiles_x, p.tiles_y);
         if (NBUF == 2) {
-            if (tile + nworkers < ntiles && !(p.dbg_flags & 4))
+            if (tile + nworkers < ntiles)
                 octet_issue_tile<S>(p, &tmap, (it & 1) ? buf0 : buf1, (it & 1) ? bar0 : bar1, nxt, type, py, px);
             cp_async_commit();
             cp_async_wait<1>();   // hash bytes: everything but the newest group (the prefetch) has landed
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
                     // pixel have read it, and only if the next pixel hashes to another bucket
                     unsigned nbucket = (b < 7) ? (((b + 1 < 4 ? hb.x : hb.y) >> (8 * ((b + 1) & 3))) & 0xffu) : (hnext.x & 0xffu);
                     nbucket = min(nbucket, maxb);
-                    const bool reload = (nbucket != bucket) || (p.dbg_flags & 1);
+                    const bool reload = nbucket != bucket;
                     bucket = nbucket;
                     const unsigned tpa = tab_lane_s + nbucket * (kOctStride * 4);
                     constexpr int MP = G::WP - 1;
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
                     lds128_if(t3, tpa + 384, reload);
                     // fresh patch values of the next pixel overwrite the slots this pixel has just consumed
                     const int npix = b0 + b + 1;
-                    if (npix < C::IW && !(p.dbg_flags & 16)) {
+                    if (npix < C::IW) {
                         const int on = S * (b + 1);
 #pragma unroll
                         for (int t = 0; t < G::NEWF; ++t) w11[(on + kFlen - G::NEWF + t) % G::WF] = pf[(S * npix + kFlen - G::NEWF + t) * G::PT];
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
                 float keep = h0 ? r2[1] : r2[0];
                 float v = keep + __shfl_xor_sync(omask, send, 1);
                 const int ox = oxs + b0 + lane8;
-                if (ox < p.ow && !(p.dbg_flags & 2)) {
+                if (ox < p.ow) {
                     if (sizeof(OutT) == 4 && p.raw_f32) *reinterpret_cast<float*>(drow + (S * ox + px)) = v;
                     else store_px(drow + (S * ox + px), v);
                 }

@@ -118,7 +118,7 @@ def test_batch_equals_single_frames(raisr):
     try:
         ms = raisr.upsample_batch(frames, out, 2)
     finally:
-        raisr.set_option("chunk_budget_bytes", 96 << 20)
+        raisr.set_option("chunk_budget_bytes", 208 << 20)
     assert len(ms) == 3
     for k in range(5):
         one = np.zeros((144, 208), np.uint8)
@@ -147,7 +147,7 @@ def test_overlapped_pipeline_matches_serial(raisr):
         dev = t_dst.cpu().numpy()
     finally:
         raisr.set_option("overlap", 0)
-        raisr.set_option("chunk_budget_bytes", 96 << 20)
+        raisr.set_option("chunk_budget_bytes", 208 << 20)
     assert np.array_equal(serial, over)
     assert np.array_equal(serial, dev)
 
