@@ -116,6 +116,23 @@ int raisr_resize_u8(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_p
                     uint8_t* dst, int dw, int dh, size_t dst_pitch, int mode, int n_frames, int where,
                     float ms[3]);
 
+/* Histogram equalisation, SURVEY.md 8(f) row N4: the device side of clHistEq (histeq/eq_opencl.py:37-89,
+ * kernels histeq/hist.cl:41-147).  8-bit gray images, `where` as above; the handle only supplies the
+ * device and stream.
+ *   ocv_hist_grid_u8            replaces clHistEq.histGrid (eq_opencl.py:37-51): 256-bin histogram of every
+ *                               256x32 tile, hist_out = uint32 (h/32, w/256, 256); remainders are ignored
+ *                               like the reference's integer divisions
+ *   ocv_histeq_global_u8        replaces clHistEq.histeqGlobal (eq_opencl.py:53-68): dst = mapping[src]
+ *   ocv_histeq_local_block_u8   replaces clHistEq.histeqLocalBlock (eq_opencl.py:70-89): bilinear blend of the
+ *                               four neighbouring block mappings, `mappings` = float32 (ny, nx, 256) */
+int ocv_hist_grid_u8(raisr_t* h, const uint8_t* img, int w, int hgt, size_t pitch, uint32_t* hist_out, int where,
+                     float ms[3]);
+int ocv_histeq_global_u8(raisr_t* h, const uint8_t* src, int w, int hgt, size_t src_pitch, uint8_t* dst,
+                         size_t dst_pitch, const uint8_t* mapping256, int where, float ms[3]);
+int ocv_histeq_local_block_u8(raisr_t* h, const uint8_t* src, int w, int hgt, size_t src_pitch, uint8_t* dst,
+                              size_t dst_pitch, const float* mappings, int nx, int ny, int block_w,
+                              int block_h, int where, float ms[3]);
+
 /* Parity probe: the per-pixel quantities of raisr.cl:278-317 for one frame.  All outputs are
  * dense dh x dw arrays in `where` memory, any may be NULL: hash (int32, full index into the
  * filter table incl. pixel type), angle (theta in [0,pi)), l1 (strength), coherence, and the

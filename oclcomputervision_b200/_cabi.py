@@ -36,6 +36,10 @@ SIGNATURES = {
                                   c_size_t, c_int, c_int, c_int, POINTER(c_float)]),
     "raisr_resize_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_void_p, c_int, c_int, c_size_t,
                                 c_int, c_int, c_int, POINTER(c_float)]),
+    "ocv_hist_grid_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_void_p, c_int, POINTER(c_float)]),
+    "ocv_histeq_global_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_void_p, c_size_t, c_void_p, c_int, POINTER(c_float)]),
+    "ocv_histeq_local_block_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_void_p, c_size_t, c_void_p, c_int, c_int,
+                                          c_int, c_int, c_int, POINTER(c_float)]),
     "raisr_debug_hash": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_int]),
     "raisr_upsample_band_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_int, c_void_p,

@@ -20,6 +20,7 @@
 
 #include "raisr_filter.cuh"
 #include "raisr_octet.cuh"
+#include "histeq.cuh"
 #include "raisr_color.cuh"
 #include "raisr_prep.cuh"
 #include "raisr_resize.cuh"
@@ -840,6 +841,115 @@ int raisr_resize_u8(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_p
         }
     }
     return 0;
+}
+
+namespace {
+
+// Shared host plumbing of the three histeq entry points: optional H2D of the image (and of a small
+// parameter blob), kernel, optional D2H of the result; fills ms[3] like get_elapsed_ms.
+struct HistIo {
+    raisr_ctx* h; cudaStream_t st; int where;
+    const uint8_t* dimg = nullptr;
+    int begin(const uint8_t* img, size_t bytes)
+    {
+        dimg = img;
+        cudaEventRecord(h->ev(0), st);
+        if (where == RAISR_HOST) {
+            if (int rc = h->dsrc[0].ensure(bytes)) return rc;
+            CUDA_TRY(cudaMemcpyAsync(h->dsrc[0].p, img, bytes, cudaMemcpyHostToDevice, st));
+            dimg = (const uint8_t*)h->dsrc[0].p;
+        }
+        return 0;
+    }
+    int finish(float ms[3])
+    {
+        if (where == RAISR_HOST || ms) {
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (ms) {
+                cudaEventElapsedTime(&ms[0], h->ev(0), h->ev(1));
+                cudaEventElapsedTime(&ms[1], h->ev(1), h->ev(2));
+                cudaEventElapsedTime(&ms[2], h->ev(2), h->ev(3));
+            }
+        }
+        return 0;
+    }
+};
+
+}  // namespace
+
+int ocv_hist_grid_u8(raisr_t* h, const uint8_t* img, int w, int hgt, size_t pitch, uint32_t* hist_out, int where, float ms[3])
+{
+    if (!h || !img || !hist_out) return fail(RAISR_E_ARG, "null argument");
+    if (w < kHistBins || hgt < kHistTileH || pitch < (size_t)w) return fail(RAISR_E_ARG, "image %dx%d smaller than one 256x32 tile", w, hgt);
+    if (where != RAISR_HOST && where != RAISR_DEVICE) return fail(RAISR_E_ARG, "where must be RAISR_HOST or RAISR_DEVICE");
+    Guard guard(h->device);
+    HistIo io{h, h->stream(), where};
+    const int tx = w / kHistBins, ty = hgt / kHistTileH;
+    const size_t out_bytes = (size_t)tx * ty * kHistBins * sizeof(uint32_t);
+    if (int rc = io.begin(img, pitch * hgt)) return rc;
+    uint32_t* dout = hist_out;
+    if (where == RAISR_HOST) {
+        if (int rc = h->dbg.ensure(out_bytes)) return rc;
+        dout = (uint32_t*)h->dbg.p;
+    }
+    cudaEventRecord(h->ev(1), io.st);
+    HistParams hp{io.dimg, pitch, dout, tx, ty};
+    hist_tiles_kernel<<<dim3(tx, ty), 256, 0, io.st>>>(hp);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    cudaEventRecord(h->ev(2), io.st);
+    if (where == RAISR_HOST) CUDA_TRY(cudaMemcpyAsync(hist_out, dout, out_bytes, cudaMemcpyDeviceToHost, io.st));
+    cudaEventRecord(h->ev(3), io.st);
+    return io.finish(ms);
+}
+
+static int histeq_apply(raisr_t* h, const uint8_t* src, int w, int hgt, size_t src_pitch, uint8_t* dst, size_t dst_pitch,
+                        const uint8_t* mapping256, const float* mappings, int nx, int ny, int bw, int bh, int where, float ms[3])
+{
+    if (!h || !src || !dst) return fail(RAISR_E_ARG, "null argument");
+    if (w < 1 || hgt < 1 || src_pitch < (size_t)w || dst_pitch < (size_t)w) return fail(RAISR_E_ARG, "bad image shape / pitch");
+    if (where != RAISR_HOST && where != RAISR_DEVICE) return fail(RAISR_E_ARG, "where must be RAISR_HOST or RAISR_DEVICE");
+    Guard guard(h->device);
+    HistIo io{h, h->stream(), where};
+    if (int rc = io.begin(src, src_pitch * hgt)) return rc;
+    uint8_t* ddst = dst;
+    const size_t table_bytes = mapping256 ? 256 : (size_t)nx * ny * kHistBins * sizeof(float);
+    const void* dtable = mapping256 ? (const void*)mapping256 : (const void*)mappings;
+    if (where == RAISR_HOST) {
+        if (int rc = h->ddst[0].ensure(dst_pitch * hgt)) return rc;
+        if (int rc = h->dbg.ensure(table_bytes)) return rc;
+        ddst = (uint8_t*)h->ddst[0].p;
+        CUDA_TRY(cudaMemcpyAsync(h->dbg.p, dtable, table_bytes, cudaMemcpyHostToDevice, io.st));
+        dtable = h->dbg.p;
+    }
+    cudaEventRecord(h->ev(1), io.st);
+    LutParams lp{io.dimg, src_pitch, ddst, dst_pitch, w, hgt, (const uint8_t*)dtable, (const float*)dtable, bw, bh, nx, ny};
+    if (mapping256) {
+        int gx = std::max(1, std::min(8, (w + 4095) / 4096));
+        lut_apply_kernel<<<dim3(gx, hgt), 256, 0, io.st>>>(lp);
+    } else {
+        lut_blend_kernel<<<dim3((w + 255) / 256, hgt), 256, 0, io.st>>>(lp);
+    }
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    cudaEventRecord(h->ev(2), io.st);
+    if (where == RAISR_HOST) CUDA_TRY(cudaMemcpyAsync(dst, ddst, dst_pitch * hgt, cudaMemcpyDeviceToHost, io.st));
+    cudaEventRecord(h->ev(3), io.st);
+    return io.finish(ms);
+}
+
+int ocv_histeq_global_u8(raisr_t* h, const uint8_t* src, int w, int hgt, size_t src_pitch, uint8_t* dst, size_t dst_pitch,
+                         const uint8_t* mapping256, int where, float ms[3])
+{
+    if (!mapping256) return fail(RAISR_E_ARG, "null mapping");
+    return histeq_apply(h, src, w, hgt, src_pitch, dst, dst_pitch, mapping256, nullptr, 0, 0, 0, 0, where, ms);
+}
+
+int ocv_histeq_local_block_u8(raisr_t* h, const uint8_t* src, int w, int hgt, size_t src_pitch, uint8_t* dst, size_t dst_pitch,
+                              const float* mappings, int nx, int ny, int block_w, int block_h, int where, float ms[3])
+{
+    if (!mappings || nx < 1 || ny < 1 || block_w < 1 || block_h < 1) return fail(RAISR_E_ARG, "bad mapping grid");
+    return histeq_apply(h, src, w, hgt, src_pitch, dst, dst_pitch, nullptr, mappings, nx, ny, block_w, block_h, where, ms);
 }
 
 int raisr_debug_hash(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_pitch, int scale, int32_t* hash,

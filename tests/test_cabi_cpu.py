@@ -14,7 +14,7 @@ from tests.conftest import HAS_GPU, ROOT
 def _declared_symbols():
     txt = open(os.path.join(ROOT, "include", "raisr_b200.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(raisr_[a-z0-9_]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b((?:raisr|ocv)_[a-z0-9_]+)\s*\(", txt)))
 
 
 def test_library_exports_every_declared_symbol():
