@@ -923,12 +923,30 @@ static int histeq_apply(raisr_t* h, const uint8_t* src, int w, int hgt, size_t s
         dtable = h->dbg.p;
     }
     cudaEventRecord(h->ev(1), io.st);
-    LutParams lp{io.dimg, src_pitch, ddst, dst_pitch, w, hgt, (const uint8_t*)dtable, (const float*)dtable, bw, bh, nx, ny};
+    LutParams lp{io.dimg, src_pitch, ddst, dst_pitch, w, hgt, (const uint8_t*)dtable, (const float*)dtable, bw, bh, nx, ny, 0, 0, 0};
+    constexpr int kLutSmem = 32 * 1024;
     if (mapping256) {
-        int gx = std::max(1, std::min(8, (w + 4095) / 4096));
-        lut_apply_kernel<<<dim3(gx, hgt), 256, 0, io.st>>>(lp);
+        static bool attr_done = false;
+        if (!attr_done) { CUDA_TRY(cudaFuncSetAttribute(lut_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutSmem)); attr_done = true; }
+        const long long chunks = (long long)((w + 15) / 16) * hgt;
+        const int ctas = (int)std::max(1LL, std::min<long long>((long long)h->sm_count * 6, (chunks + 2047) / 2048));
+        lut_apply_kernel<<<ctas, 256, kLutSmem, io.st>>>(lp);
     } else {
-        lut_blend_kernel<<<dim3((w + 255) / 256, hgt), 256, 0, io.st>>>(lp);
+        static bool attr_done = false;
+        constexpr int kBlendSmem = kLutSmem + 4096;
+        if (!attr_done) { CUDA_TRY(cudaFuncSetAttribute(lut_blend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlendSmem)); attr_done = true; }
+        // cell k = pixels whose upper-left block index is k; the last cell runs to the image edge
+        lp.cells_x = std::min(nx, std::max(0, w - 1 - bw / 2) / bw + 1);
+        lp.cells_y = std::min(ny, std::max(0, hgt - 1 - bh / 2) / bh + 1);
+        int max_rows = 0;
+        for (int k = 0; k < lp.cells_y; ++k) {
+            const int lo = k ? k * bh + bh / 2 : 0, hi = (k == lp.cells_y - 1) ? hgt : (k + 1) * bh + bh / 2;
+            max_rows = std::max(max_rows, hi - lo);
+        }
+        lp.strips = (max_rows + kBlendStripRows - 1) / kBlendStripRows;
+        const long long jobs = (long long)lp.cells_x * lp.cells_y * lp.strips;
+        if (jobs > 0x7fffffffLL) return fail(RAISR_E_ARG, "too many blocks");
+        lut_blend_kernel<<<(unsigned)jobs, 256, kBlendSmem, io.st>>>(lp);
     }
     h->launches++;
     CUDA_TRY(cudaGetLastError());

@@ -50,7 +50,7 @@ class clHistEq:
     def __init__(self, device: int = 0):
         self._lib = _cabi.load()
         h = ctypes.c_void_p()
-        _cabi.check(self._lib.raisr_create(int(device), ctypes.byref(h)))
+        _cabi.check(self._lib.raisr_create(ctypes.byref(h), int(device), 24, 3, 3, 11))
         self._h = h
         self.HIST_BINS = HIST_BINS
         self.HIST_THREAD_NUM = HIST_THREAD_NUM

@@ -68,6 +68,9 @@ def _block_geometry(n, block, nblocks):
     pos = np.arange(n)
     num = pos - block // 2
     b0 = np.where(num >= 0, num // block, -((-num) // block))     # C division truncates toward zero
+    # an image wider than nblocks*block + block/2 makes the reference index one block past its tables
+    # (undefined there); here such pixels stay in the last block, with the weight saturating at 1
+    b0 = np.minimum(b0, nblocks - 1)
     centre = b0 * block + block // 2
     b1 = np.minimum(b0 + 1, nblocks - 1)
     return pos, b0, b1, centre
@@ -83,7 +86,6 @@ def local_block_apply(gray: np.ndarray, maps: np.ndarray, blockshape) -> np.ndar
     y, by0, by1, cy = _block_geometry(h, bh, ny)
     s = np.clip((x - cx).astype(f32) / f32(bw), f32(0), f32(1))[None, :]
     t = np.clip((y - cy).astype(f32) / f32(bh), f32(0), f32(1))[:, None]
-    bx0 = np.minimum(bx0, nx - 1); by0 = np.minimum(by0, ny - 1)   # only differs where the reference reads out of bounds
     v = gray.astype(np.intp)
     f00 = maps[by0[:, None], bx0[None, :], v]
     f01 = maps[by0[:, None], bx1[None, :], v]

@@ -110,7 +110,8 @@ def test_gpu_global_and_local_match_reference_golden(cleq):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape,block", [((1080, 1920), (256, 256)), ((2160, 3840), (256, 256)),
-                                         ((777, 1031), (128, 256)), ((2160, 3840), (96, 512))])
+                                         ((777, 1031), (128, 256)), ((2160, 3840), (96, 512)),
+                                         ((300, 700), (128, 256)), ((256, 256), (256, 256)), ((511, 1023), (224, 512))])
 def test_gpu_local_block_vs_oracle(cleq, shape, block):
     from oclcomputervision_b200 import histeq
     g = golden_image(shape[0], shape[1], 21)

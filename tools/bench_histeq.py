@@ -21,7 +21,7 @@ def main():
     a = ap.parse_args()
     lib = _cabi.load()
     h = ctypes.c_void_p()
-    _cabi.check(lib.raisr_create(0, ctypes.byref(h)))
+    _cabi.check(lib.raisr_create(ctypes.byref(h), 0, 24, 3, 3, 11))
     n = a.size
     peaks = {}
     try:
