@@ -67,7 +67,13 @@ int raisr_set_stream(raisr_t* h, void* cuda_stream);
 /* Tuning knobs without a reference counterpart.  Keys: "filter_impl" (1 = octet kernel, default;
  * 0 = block kernel), "chunk_budget_bytes" (size of the per-launch upscaled-image scratch, default 208 MiB),
  * "overlap" (1 = experimental two-stream pipeline that co-schedules the prep kernel of the next chunk
- * with the filter kernel of the current one; default 0, slower on B200). */
+ * with the filter kernel of the current one; default 0, slower on B200).
+ * Semantics switches, both default 0 = the intended fp32 algorithm:
+ *   "quirks"    1 = "as written": the three slips of the shipped kernel text are reproduced --
+ *               ma accumulates gx*gy (raisr.cl:271), the coherence bucket compares L1 (raisr.cl:310),
+ *               strength is left out of the hash (raisr.cl:316)
+ *   "taps_fp16" 1 = every tap is rounded to fp16 before use, as the reference's `(half)pf[...]`
+ *               (raisr.cl:328) does; arithmetic stays fp32.  Re-packs the tables already set. */
 int raisr_set_option(raisr_t* h, const char* key, long long value);
 
 /* Replaces ClRaisr.upsample (raisr.py:85-135) for gray frames: H2D copy, the fused RAISR kernels

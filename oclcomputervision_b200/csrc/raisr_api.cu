@@ -20,6 +20,7 @@
 
 #include "raisr_filter.cuh"
 #include "raisr_octet.cuh"
+#include <cuda_fp16.h>
 #include "histeq.cuh"
 #include "raisr_color.cuh"
 #include "raisr_prep.cuh"
@@ -76,6 +77,7 @@ struct DevBuf {
 struct ScaleTable {
     DevBuf block;   // [type][bucket][132]  (filter_block_kernel)
     DevBuf octet;   // [type][bucket][128]  (filter_octet_kernel, lane-major chunks)
+    std::vector<float> host;  // the caller's table as given (repacked when the tap precision option changes)
     bool set = false;
 };
 
@@ -101,6 +103,8 @@ struct raisr_ctx {
     long long launches = 0;
     float last_prep_ms = 0, last_filter_ms = 0;
     int filter_impl = 1;  // 0 = block (v1), 1 = octet
+    int as_written = 0;   // "quirks" option
+    int taps_fp16 = 0;    // "taps_fp16" option
     size_t chunk_budget = 208u << 20;   // upscaled-image scratch per kernel launch: 6 frames of 1080p->4K
 
     cudaStream_t stream() const { return use_user_stream ? user_stream : own_stream; }
@@ -328,7 +332,7 @@ void fill_params(raisr_ctx* h, const Geometry& g, const uint8_t* dsrc, int sw, i
     pp.uext = uext; pp.uext_pitch = g.uext_pitch; pp.uext_frame_stride = g.uext_frame;
     pp.hash = hash; pp.hash_pitch = g.hash_pitch; pp.hash_plane_stride = g.hash_plane;
     pp.hash_frame_stride = g.hash_frame;
-    pp.n_angle = h->n_angle; pp.n_strength = h->n_strength; pp.n_coherence = h->n_coherence;
+    pp.n_angle = h->n_angle; pp.n_strength = h->n_strength; pp.n_coherence = h->n_coherence; pp.as_written = h->as_written;
     memcpy(pp.sq, h->sq, sizeof(pp.sq)); memcpy(pp.cq, h->cq, sizeof(pp.cq));
     fp = FilterParams{};
     fp.uext = pp.uext; fp.uext_pitch = g.uext_pitch; fp.uext_frame_stride = g.uext_frame;
@@ -587,15 +591,20 @@ void raisr_destroy(raisr_t* h)
     delete h;
 }
 
-int raisr_set_filters(raisr_t* h, int scale, const float* table, size_t n_floats)
+// Packs the caller's table (layout raisr.cl:316-317) into the two device layouts.  With taps_fp16 every
+// tap is first rounded to fp16 and back: the reference multiplies by `(half)pf[...]` (raisr.cl:328).
+static int upload_table(raisr_ctx* h, int scale)
 {
-    if (!h || !table) return fail(RAISR_E_ARG, "null argument");
-    if (scale < 2 || scale > 4) return fail(RAISR_E_UNSUPPORTED, "scale %d not supported (2, 3 or 4)", scale);
     const int ss = scale * scale, nb = h->n_buckets;
-    const size_t want = (size_t)nb * ss * kTaps;
-    if (n_floats != want) return fail(RAISR_E_ARG, "filter table has %zu floats, expected %zu = %d*%d*%d*%d*121", n_floats, want, h->n_angle, h->n_strength, h->n_coherence, ss);
     Guard guard(h->device);
     ScaleTable& t = h->tables[scale];
+    std::vector<float> q;
+    const float* table = t.host.data();
+    if (h->taps_fp16) {
+        q.resize(t.host.size());
+        for (size_t i = 0; i < q.size(); ++i) q[i] = __half2float(__float2half_rn(t.host[i]));
+        table = q.data();
+    }
     // block layout: [type][bucket][row i][12]; octet layout: see raisr_octet.cuh
     std::vector<float> blk((size_t)ss * nb * kFStride, 0.0f), oct((size_t)ss * nb * kOctStride, 0.0f);
     for (int type = 0; type < ss; ++type)
@@ -608,10 +617,22 @@ int raisr_set_filters(raisr_t* h, int scale, const float* table, size_t n_floats
         }
     if (int rc = t.block.ensure(blk.size() * sizeof(float))) return rc;
     if (int rc = t.octet.ensure(oct.size() * sizeof(float))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->stream()));   // a previous launch may still read the old table
     CUDA_TRY(cudaMemcpy(t.block.p, blk.data(), blk.size() * sizeof(float), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(t.octet.p, oct.data(), oct.size() * sizeof(float), cudaMemcpyHostToDevice));
     t.set = true;
     return 0;
+}
+
+int raisr_set_filters(raisr_t* h, int scale, const float* table, size_t n_floats)
+{
+    if (!h || !table) return fail(RAISR_E_ARG, "null argument");
+    if (scale < 2 || scale > 4) return fail(RAISR_E_UNSUPPORTED, "scale %d not supported (2, 3 or 4)", scale);
+    const int ss = scale * scale, nb = h->n_buckets;
+    const size_t want = (size_t)nb * ss * kTaps;
+    if (n_floats != want) return fail(RAISR_E_ARG, "filter table has %zu floats, expected %zu = %d*%d*%d*%d*121", n_floats, want, h->n_angle, h->n_strength, h->n_coherence, ss);
+    h->tables[scale].host.assign(table, table + n_floats);
+    return upload_table(h, scale);
 }
 
 int raisr_set_quantizers(raisr_t* h, const float* strength_q, int n_sq, const float* coherence_q, int n_cq)
@@ -637,6 +658,17 @@ int raisr_set_option(raisr_t* h, const char* key, long long value)
     if (!h || !key) return fail(RAISR_E_ARG, "null argument");
     if (!strcmp(key, "filter_impl")) { h->filter_impl = value ? 1 : 0; return 0; }
     if (!strcmp(key, "overlap")) { h->overlap = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "quirks")) { h->as_written = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "taps_fp16")) {
+        const int v = value ? 1 : 0;
+        if (v != h->taps_fp16) {
+            h->taps_fp16 = v;
+            for (int sc = 2; sc <= 4; ++sc)
+                if (h->tables[sc].set)
+                    if (int rc = upload_table(h, sc)) return rc;
+        }
+        return 0;
+    }
     if (!strcmp(key, "chunk_budget_bytes")) { h->chunk_budget = (size_t)std::max<long long>(value, 1 << 20); return 0; }
     return fail(RAISR_E_ARG, "unknown option %s", key);
 }
@@ -1000,7 +1032,7 @@ int raisr_debug_hash(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_
     pp.uext = (float*)h->uext.p; pp.uext_pitch = g.uext_pitch; pp.uext_frame_stride = g.uext_frame;
     pp.hash = (uint8_t*)h->hash.p; pp.hash_pitch = g.hash_pitch; pp.hash_plane_stride = g.hash_plane;
     pp.hash_frame_stride = g.hash_frame;
-    pp.n_angle = h->n_angle; pp.n_strength = h->n_strength; pp.n_coherence = h->n_coherence;
+    pp.n_angle = h->n_angle; pp.n_strength = h->n_strength; pp.n_coherence = h->n_coherence; pp.as_written = h->as_written;
     memcpy(pp.sq, h->sq, sizeof(pp.sq)); memcpy(pp.cq, h->cq, sizeof(pp.cq));
     pp.dbg_hash = (int32_t*)dev[0]; pp.dbg_angle = (float*)dev[1]; pp.dbg_l1 = (float*)dev[2];
     pp.dbg_coh = (float*)dev[3]; pp.dbg_u = (float*)dev[4]; pp.dbg_pitch = dw;
@@ -1055,7 +1087,7 @@ int raisr_upsample_band_u8(raisr_t* h, const uint8_t* src_rows_ptr, int sw, int 
     pp.uext = (float*)h->uext.p; pp.uext_pitch = g.uext_pitch; pp.uext_frame_stride = g.uext_frame;
     pp.hash = (uint8_t*)h->hash.p; pp.hash_pitch = g.hash_pitch; pp.hash_plane_stride = g.hash_plane;
     pp.hash_frame_stride = g.hash_frame;
-    pp.n_angle = h->n_angle; pp.n_strength = h->n_strength; pp.n_coherence = h->n_coherence;
+    pp.n_angle = h->n_angle; pp.n_strength = h->n_strength; pp.n_coherence = h->n_coherence; pp.as_written = h->as_written;
     memcpy(pp.sq, h->sq, sizeof(pp.sq)); memcpy(pp.cq, h->cq, sizeof(pp.cq));
     if (int rc = launch_prep(h, pp, scale, st, false)) return rc;
     FilterParams fp{};

@@ -56,15 +56,25 @@ class ClRaisr:
 
     def __init__(self, grayMode, filters: Optional[np.ndarray] = None, device: int = 0,
                  n_angle: int = 24, n_strength: int = 3, n_coherence: int = 3,
-                 filter_path: Optional[str] = None):
+                 filter_path: Optional[str] = None, quirks: str = "intended", taps: str = "fp32"):
+        """quirks="as_written" reproduces the three slips of the kernel text (raisr.cl:271,310,316);
+        taps="fp16" rounds every tap to half precision like the reference's `(half)pf[...]` (raisr.cl:328).
+        Both default to the intended fp32 algorithm; arithmetic is fp32 in every mode."""
         if grayMode not in (0, 1):
             raise ValueError("grayMode must be 1 (gray, raisr.py:97-100) or 0 (BGRA, raisr.py:101-104)")
+        if quirks not in ("intended", "as_written") or taps not in ("fp32", "fp16"):
+            raise ValueError("quirks must be 'intended' or 'as_written', taps 'fp32' or 'fp16'")
         self.grayMode = grayMode
         self.n_angle, self.n_strength, self.n_coherence = n_angle, n_strength, n_coherence
         self._lib = _cabi.load()
         self._h = ctypes.c_void_p()
         _cabi.check(self._lib.raisr_create(ctypes.byref(self._h), device, n_angle, n_strength, n_coherence, 11))
         self._filters = {}
+        self.quirks, self.taps = quirks, taps
+        if quirks == "as_written":
+            self.set_option("quirks", 1)
+        if taps == "fp16":
+            self.set_option("taps_fp16", 1)
         # raisr.py:80-82
         g = self.gaussian2d([9, 9], 2)
         g = np.diag(g.ravel()).astype(np.float32)

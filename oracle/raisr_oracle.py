@@ -128,8 +128,14 @@ def tensor(Uext: np.ndarray):
 
 
 def eigen_hash(ma, mb, md, s, n_angle=24, n_strength=3, n_coherence=3,
-               strength_q=DEFAULT_STRENGTH_Q, coherence_q=DEFAULT_COHERENCE_Q):
-    """Stages 5-6 (raisr.cl:278-317), intended semantics."""
+               strength_q=DEFAULT_STRENGTH_Q, coherence_q=DEFAULT_COHERENCE_Q, quirks="intended"):
+    """Stages 5-6 (raisr.cl:278-317).  quirks="intended" (default) or "as_written": the literal kernel
+    text, i.e. ma = sum w*gx*gy (raisr.cl:271), coherence bucket compares L1 (raisr.cl:310) and strength
+    is left out of the hash (raisr.cl:316)."""
+    assert quirks in ("intended", "as_written")
+    literal = quirks == "as_written"
+    if literal:
+        ma = mb
     with np.errstate(invalid="ignore", divide="ignore"):
         T = ma + md
         D = ma * md - mb * mb
@@ -154,7 +160,9 @@ def eigen_hash(ma, mb, md, s, n_angle=24, n_strength=3, n_coherence=3,
         si = np.where(L1 < sq_[i], i, si)
     ci = np.full(a.shape, n_coherence - 1, np.int32)
     for i in range(n_coherence - 2, -1, -1):
-        ci = np.where(coh < cq_[i], i, ci)
+        ci = np.where((L1 if literal else coh) < cq_[i], i, ci)
+    if literal:
+        si = np.zeros_like(si)
     dh, dw = a.shape
     yy, xx = np.mgrid[0:dh, 0:dw]
     ptype = (yy % s) * s + (xx % s)
@@ -176,13 +184,21 @@ def gather_dot(Uext, hash_, filters):
 
 def raisr_ref(src_u8: np.ndarray, filters: Optional[np.ndarray], s: int = 2, *,
               n_angle=24, n_strength=3, n_coherence=3,
-              strength_q=DEFAULT_STRENGTH_Q, coherence_q=DEFAULT_COHERENCE_Q) -> Dict[str, np.ndarray]:
-    """numpy restatement.  Returns U, Uext, angle, L1, coherence, hash, out_f32, out_u8."""
+              strength_q=DEFAULT_STRENGTH_Q, coherence_q=DEFAULT_COHERENCE_Q,
+              quirks: str = "intended", taps: str = "fp32") -> Dict[str, np.ndarray]:
+    """numpy restatement.  Returns U, Uext, angle, L1, coherence, hash, out_f32, out_u8.
+
+    quirks: "intended" | "as_written" (see eigen_hash).  taps: "fp32" | "fp16" -- "fp16" rounds every tap
+    to half precision first, as the reference's `(half)pf[i*FILTER_LEN+j]` does (raisr.cl:328); the
+    arithmetic stays fp32 either way."""
+    assert taps in ("fp32", "fp16")
     src_u8 = np.ascontiguousarray(src_u8, dtype=np.uint8)
     Uext = upscale_ext(src_u8, s)
     ma, mb, md = tensor(Uext)
     theta, L1, coh, h = eigen_hash(ma, mb, md, s, n_angle, n_strength, n_coherence,
-                                   strength_q, coherence_q)
+                                   strength_q, coherence_q, quirks)
+    if filters is not None and taps == "fp16":
+        filters = np.asarray(filters, dtype=F32).astype(np.float16).astype(F32)
     res = dict(Uext=Uext, U=Uext[MARGIN:-MARGIN, MARGIN:-MARGIN].copy(), angle=theta, L1=L1,
                coherence=coh, hash=h, ma=ma, mb=mb, md=md)
     if filters is not None:
@@ -194,15 +210,18 @@ def raisr_ref(src_u8: np.ndarray, filters: Optional[np.ndarray], s: int = 2, *,
 
 
 def edge_distance(res: Dict[str, np.ndarray], n_angle=24,
-                  strength_q=DEFAULT_STRENGTH_Q, coherence_q=DEFAULT_COHERENCE_Q) -> np.ndarray:
+                  strength_q=DEFAULT_STRENGTH_Q, coherence_q=DEFAULT_COHERENCE_Q, quirks="intended") -> np.ndarray:
     """Per-pixel distance of the float angle*n/pi, L1 and coherence to their nearest bin edge
-    (the quantity north_star excuses below 1e-5)."""
+    (the quantity north_star excuses below 1e-5).  With quirks="as_written" the only thresholds that reach
+    the hash are the angle bins and L1 against the *coherence* quantisers."""
     a = (res["angle"].astype(np.float64) / np.pi) * n_angle
     da = np.abs(a - np.rint(a))
     l1 = res["L1"].astype(np.float64)
     ds = np.min([np.abs(l1 - float(q)) for q in strength_q], axis=0)
     co = res["coherence"].astype(np.float64)
     dc = np.min([np.abs(co - float(q)) for q in coherence_q], axis=0)
+    if quirks == "as_written":
+        return np.minimum(da, np.min([np.abs(l1 - float(q)) for q in coherence_q], axis=0))
     return np.minimum(np.minimum(da, ds), dc)
 
 
@@ -232,6 +251,8 @@ def _load():
         lib.raisr_oracle_run.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_int,
                                          vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp,
                                          vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int]
+        lib.raisr_oracle_run_ex.restype = ctypes.c_int
+        lib.raisr_oracle_run_ex.argtypes = list(lib.raisr_oracle_run.argtypes) + [ctypes.c_int, ctypes.c_int]
         lib.raisr_oracle_bilinear_u8.restype = ctypes.c_int
         lib.raisr_oracle_bilinear_u8.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t,
                                                  ctypes.c_int, vp]
@@ -254,8 +275,10 @@ def raisr_ref_c(src_u8: np.ndarray, filters: Optional[np.ndarray], s: int = 2, *
                 n_angle=24, n_strength=3, n_coherence=3,
                 strength_q=DEFAULT_STRENGTH_Q, coherence_q=DEFAULT_COHERENCE_Q,
                 nthreads: int = 0, want=("U", "Uext", "angle", "L1", "coherence", "hash",
-                                         "out_f32", "out_u8")) -> Dict[str, np.ndarray]:
-    """C restatement (oracle/raisr_oracle.c).  Same keys as raisr_ref."""
+                                         "out_f32", "out_u8"),
+                quirks: str = "intended", taps: str = "fp32") -> Dict[str, np.ndarray]:
+    """C restatement (oracle/raisr_oracle.c).  Same keys and options as raisr_ref."""
+    assert quirks in ("intended", "as_written") and taps in ("fp32", "fp16")
     lib = _load()
     src_u8 = np.ascontiguousarray(src_u8, dtype=np.uint8)
     sh, sw = src_u8.shape
@@ -279,11 +302,12 @@ def raisr_ref_c(src_u8: np.ndarray, filters: Optional[np.ndarray], s: int = 2, *
     def ptr(k):
         return res[k].ctypes.data if k in res else None
 
-    rc = lib.raisr_oracle_run(src_u8.ctypes.data, sw, sh, src_u8.strides[0], s,
-                              flt.ctypes.data if flt is not None else None,
-                              n_angle, n_strength, n_coherence, sq.ctypes.data, cq.ctypes.data,
-                              ptr("U"), ptr("Uext"), ptr("angle"), ptr("L1"), ptr("coherence"),
-                              ptr("hash"), ptr("out_f32"), ptr("out_u8"), int(nthreads))
+    rc = lib.raisr_oracle_run_ex(src_u8.ctypes.data, sw, sh, src_u8.strides[0], s,
+                                 flt.ctypes.data if flt is not None else None,
+                                 n_angle, n_strength, n_coherence, sq.ctypes.data, cq.ctypes.data,
+                                 ptr("U"), ptr("Uext"), ptr("angle"), ptr("L1"), ptr("coherence"),
+                                 ptr("hash"), ptr("out_f32"), ptr("out_u8"), int(nthreads),
+                                 int(quirks == "as_written"), int(taps == "fp16"))
     if rc != 0:
         raise RuntimeError("raisr_oracle_run failed (%d)" % rc)
     return res

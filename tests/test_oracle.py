@@ -162,3 +162,29 @@ def test_synthetic_recipe_reaches_every_bucket():
     strength = ((h // 4) // 3) % 3
     frac = np.bincount(strength.ravel(), minlength=3) / strength.size
     assert (frac > 0.15).all()
+
+
+def test_oracle_quirks_and_taps_switches():
+    """quirks="as_written" / taps="fp16" exist in both restatements and agree with each other."""
+    from oclcomputervision_b200.synth import random_filters, synthetic_frame
+    src = synthetic_frame(40, 56, seed=3)
+    flt = random_filters(2, seed=1)
+    base = O.raisr_ref(src, flt, 2)
+    for quirks, taps in (("as_written", "fp32"), ("intended", "fp16"), ("as_written", "fp16")):
+        a = O.raisr_ref(src, flt, 2, quirks=quirks, taps=taps)
+        b = O.raisr_ref_c(src, flt, 2, quirks=quirks, taps=taps)
+        same = a["hash"] == b["hash"]
+        assert same.mean() > 0.999 and (same | (O.edge_distance(a, quirks=quirks) < 1e-5)).all()
+        assert np.abs(a["out_f32"] - b["out_f32"])[same].max() <= 1e-6
+        if quirks == "as_written":
+            # strength never reaches the hash: bucket = (angle*3 + 0)*3 + coherence bin
+            bucket = a["hash"] // 4
+            assert ((bucket // 3) % 3 == 0).all()
+            assert (a["hash"] != base["hash"]).mean() > 0.2
+        else:
+            assert np.array_equal(a["hash"], base["hash"])
+            d = np.abs(a["out_f32"] - base["out_f32"]).max()
+            assert 0 < d < 5e-3          # fp16 rounding of the taps: visible, small
+    # fp16 taps == running with a table that was rounded beforehand
+    q = flt.astype(np.float16).astype(np.float32)
+    assert np.array_equal(O.raisr_ref(src, q, 2)["out_f32"], O.raisr_ref(src, flt, 2, taps="fp16")["out_f32"])

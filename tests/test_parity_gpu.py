@@ -225,3 +225,36 @@ def test_colour_bgra_path_against_oracle(shape, s):
     assert bad.mean() < 2e-4
     assert (np.abs(dst.astype(int) - ref["out_u8"].astype(int)).max(axis=2)[~bad] <= 1).all()
     r.close()
+
+
+# ---------------------------------------------------------------- semantics switches of SURVEY.md 8(c)
+@pytest.mark.gpu
+@pytest.mark.parametrize("quirks,taps", [("as_written", "fp32"), ("intended", "fp16"), ("as_written", "fp16")])
+@pytest.mark.parametrize("scale", [2, 3])
+def test_quirks_and_fp16_taps_against_oracle(quirks, taps, scale):
+    """`quirks="as_written"` (raisr.cl:271,310,316) and `taps="fp16"` (raisr.cl:328) follow the oracle's
+    switches of the same name: hash identical away from bin edges, pixels within 1e-4 / 1 LSB."""
+    from oclcomputervision_b200.synth import random_filters, synthetic_frame
+    ro = O
+    src = synthetic_frame(120, 168, seed=31)
+    flt = random_filters(scale, seed=5)
+    want = ro.raisr_ref_c(src, flt, scale, quirks=quirks, taps=taps)
+    base = ro.raisr_ref_c(src, flt, scale)
+    assert (want["hash"] != base["hash"]).mean() > 0.2 if quirks == "as_written" else True
+    assert not np.array_equal(want["out_f32"], base["out_f32"])          # the switch does something
+    r = ClRaisr(1, device=0, quirks=quirks, taps=taps)
+    setattr(r, "filters_x%d" % scale, flt)
+    got_hash = r.debug_hash(src, scale)[0]
+    bad = got_hash != want["hash"]
+    near = ro.edge_distance(want, quirks=quirks) < 1e-5
+    assert not (bad & ~near).any(), "%d unexcused hash mismatches" % int((bad & ~near).sum())
+    out_f32 = r.upsample_f32(src, scale)
+    ok = ~bad
+    assert np.abs(out_f32 - want["out_f32"])[ok].max() <= 1e-4
+    dst = np.empty((src.shape[0] * scale, src.shape[1] * scale), np.uint8)
+    r.upsample(src, dst, scale)
+    assert np.abs(dst.astype(int) - want["out_u8"].astype(int))[ok].max() <= 1
+    # switching the tap precision back re-packs the table
+    r.set_option("taps_fp16", 0)
+    r.set_option("quirks", 0)
+    assert np.abs(r.upsample_f32(src, scale) - base["out_f32"])[r.debug_hash(src, scale)[0] == base["hash"]].max() <= 1e-4
