@@ -22,6 +22,7 @@ import os
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 import numpy as np
@@ -67,11 +68,33 @@ def cpu_baseline(budget_s=12.0):
 
 
 class ClockSampler:
+    """SM clock / throttle reasons of one GPU DURING the timed region.  NVML in a thread (a sample every
+    few ms, so even a 50 ms region is covered); falls back to an `nvidia-smi -lms` child process."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None, period_s=0.004):
+        self.rows, self.p, self.thread, self.nv = [], None, None, None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(int(index))
+            self.nv, self.h = pynvml, h
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._loop, args=(period_s,), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nv = None
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
@@ -80,7 +103,31 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def _loop(self, period_s):
+        nv, h = self.nv, self.h
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                r = int(get_reasons(h))
+                self.rows.append((sm, pw, [k for k, b in bits.items() if r & b]))
+            except Exception:
+                pass
+            self._stop.wait(period_s)
+
     def stop(self):
+        if self.nv is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            if not self.rows:
+                return dict(sm_mhz=None, sm_max_mhz=self.mx, reasons=["no samples"])
+            sm = [r[0] for r in self.rows]; pw = [r[1] for r in self.rows]
+            reasons = sorted({k for r in self.rows for k in r[2]})
+            busy = [s_ for s_, p_ in zip(sm, pw) if p_ > 0.5 * max(pw)] or sm
+            return dict(sm_mhz=float(np.median(busy)), sm_max_mhz=self.mx, samples=len(sm), power_w_max=float(max(pw)),
+                        reasons=reasons, source="nvml")
         if self.p is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.p.terminate()
@@ -102,9 +149,9 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
-        busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+        busy = [s_ for s_, p_ in zip(sm, pw) if p_ > 0.5 * max(pw)] or sm
         return dict(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)), samples=len(sm),
-                    power_w_max=float(max(pw)), reasons=sorted(reasons))
+                    power_w_max=float(max(pw)), reasons=sorted(reasons), source="nvidia-smi")
 
 
 def run_reference(args, rank, world):
@@ -181,7 +228,7 @@ def main():
         step(False)
     barrier()
     launches0 = r.launch_count()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, uuid=getattr(torch.cuda.get_device_properties(local_rank), "uuid", None))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     prep_ms = filt_ms = 0.0
     barrier()

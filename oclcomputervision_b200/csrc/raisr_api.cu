@@ -730,6 +730,42 @@ int raisr_bilinear_u8(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src
     return 0;
 }
 
+// One BGRA frame on stream `st`: upscale + CSC, hash from Y, the hashed filter on the four planes, CSC back + pack.
+static int enqueue_bgra_frame(raisr_ctx* h, const Geometry& g, const uint8_t* dsrc, int sw, int sh, size_t src_pitch, unsigned char* ddst,
+                              size_t dst_pitch, int dw, int dh, int scale, bool f32, cudaStream_t st)
+{
+    const size_t fpitch = round_up((size_t)dw, 4), fplane = fpitch * dh;
+    ColorUpParams cu{};
+    cu.src = dsrc; cu.src_pitch = src_pitch;
+    cu.sw = sw; cu.sh = sh; cu.dw = dw; cu.dh = dh; cu.pitch = g.uext_pitch;
+    for (int k = 0; k < 4; ++k) cu.plane[k] = (float*)h->uext.p + g.uext_frame * k;
+    dim3 gu((dw + 2 * kMargin + 255) / 256, (dh + 2 * kMargin + 3) / 4);
+    color_upscale_kernel<<<gu, 256, 0, st>>>(cu);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    PrepParams pp;
+    FilterParams fp;
+    fill_params(h, g, dsrc, sw, sh, src_pitch, h->cplanes.p, fpitch * sizeof(float), scale, 0, 1, (float*)h->uext.p, (uint8_t*)h->hash.p, pp, fp);
+    pp.uext_in = (const float*)h->uext.p;   // Y plane
+    if (int rc = launch_prep(h, pp, scale, st, false)) return rc;
+    for (int k = 0; k < 4; ++k) {
+        fp.uext = (const float*)h->uext.p + g.uext_frame * k;
+        fp.dst = (float*)h->cplanes.p + fplane * k;
+        fp.raw_f32 = 1;
+        if (int rc = launch_filter<float>(h, fp, scale, st)) return rc;
+    }
+    ColorPackParams cp{};
+    for (int k = 0; k < 4; ++k) cp.plane[k] = (const float*)h->cplanes.p + fplane * k;
+    cp.pitch = fpitch; cp.dw = dw; cp.dh = dh;
+    if (f32) { cp.dst_f32 = (float*)ddst; cp.dst_f32_pitch = dst_pitch / 4; }
+    else { cp.dst = ddst; cp.dst_pitch = dst_pitch; }
+    dim3 gp((dw + 255) / 256, dh);
+    color_pack_kernel<<<gp, 256, 0, st>>>(cp);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 static int upsample_bgra_impl(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_pitch, uint8_t* dst_u8, float* dst_f32, int dw,
                               int dh, size_t dst_pitch, int scale, int n_frames, int where, float ms[3])
 {
@@ -743,70 +779,64 @@ static int upsample_bgra_impl(raisr_t* h, const uint8_t* src, int sw, int sh, si
     if (dw != sw * scale || dh != sh * scale) return fail(RAISR_E_ARG, "dst shape %dx%d is not %d x src shape %dx%d", dw, dh, scale, sw, sh);
     if ((src_pitch & 3) || (dst_pitch & 3)) return fail(RAISR_E_ARG, "BGRA pitches must be multiples of 4 bytes");
     if (h->filter_impl != 1) return fail(RAISR_E_UNSUPPORTED, "the colour path needs the octet filter kernel");
+    if (where != RAISR_HOST && where != RAISR_DEVICE) return fail(RAISR_E_ARG, "where must be RAISR_HOST or RAISR_DEVICE");
     Guard guard(h->device);
-    cudaStream_t st = h->stream();
     Geometry g = make_geometry(sw, dh, scale);
     const size_t src_frame = src_pitch * sh, dst_frame = dst_pitch * dh;
     const size_t fpitch = round_up((size_t)dw, 4), fplane = fpitch * dh;
     if (int rc = h->uext.ensure(g.uext_frame * sizeof(float) * 4)) return rc;
     if (int rc = h->hash.ensure(g.hash_frame)) return rc;
     if (int rc = h->cplanes.ensure(fplane * sizeof(float) * 4)) return rc;
-    const uint8_t* dsrc = src;
-    unsigned char* ddst = (unsigned char*)dst;
-    if (where == RAISR_HOST) {
-        if (int rc = h->dsrc[0].ensure(src_frame * n_frames)) return rc;
-        if (int rc = h->ddst[0].ensure(dst_frame * n_frames)) return rc;
-        dsrc = (const uint8_t*)h->dsrc[0].p; ddst = (unsigned char*)h->ddst[0].p;
-        cudaEventRecord(h->ev(0), st);
-        CUDA_TRY(cudaMemcpyAsync(h->dsrc[0].p, src, src_frame * n_frames, cudaMemcpyHostToDevice, st));
-    } else if (where != RAISR_DEVICE) {
-        return fail(RAISR_E_ARG, "where must be RAISR_HOST or RAISR_DEVICE");
-    }
-    cudaEventRecord(h->ev(1), st);
-    for (int f = 0; f < n_frames; ++f) {
-        ColorUpParams cu{};
-        cu.src = dsrc + (size_t)f * src_frame; cu.src_pitch = src_pitch;
-        cu.sw = sw; cu.sh = sh; cu.dw = dw; cu.dh = dh; cu.pitch = g.uext_pitch;
-        for (int k = 0; k < 4; ++k) cu.plane[k] = (float*)h->uext.p + g.uext_frame * k;
-        dim3 gu((dw + 2 * kMargin + 255) / 256, (dh + 2 * kMargin + 3) / 4);
-        color_upscale_kernel<<<gu, 256, 0, st>>>(cu);
-        h->launches++;
-        CUDA_TRY(cudaGetLastError());
-        PrepParams pp;
-        FilterParams fp;
-        fill_params(h, g, dsrc, sw, sh, src_pitch, h->cplanes.p, fpitch * sizeof(float), scale, 0, 1, (float*)h->uext.p, (uint8_t*)h->hash.p, pp, fp);
-        pp.uext_in = (const float*)h->uext.p;   // Y plane
-        if (int rc = launch_prep(h, pp, scale, st, false)) return rc;
-        for (int k = 0; k < 4; ++k) {
-            fp.uext = (const float*)h->uext.p + g.uext_frame * k;
-            fp.dst = (float*)h->cplanes.p + fplane * k;
-            fp.raw_f32 = 1;
-            if (int rc = launch_filter<float>(h, fp, scale, st)) return rc;
-        }
-        ColorPackParams cp{};
-        for (int k = 0; k < 4; ++k) cp.plane[k] = (const float*)h->cplanes.p + fplane * k;
-        cp.pitch = fpitch; cp.dw = dw; cp.dh = dh;
-        if (f32) { cp.dst_f32 = (float*)(ddst + (size_t)f * dst_frame); cp.dst_f32_pitch = dst_pitch / 4; }
-        else { cp.dst = ddst + (size_t)f * dst_frame; cp.dst_pitch = dst_pitch; }
-        dim3 gp((dw + 255) / 256, dh);
-        color_pack_kernel<<<gp, 256, 0, st>>>(cp);
-        h->launches++;
-        CUDA_TRY(cudaGetLastError());
-    }
-    cudaEventRecord(h->ev(2), st);
-    if (where == RAISR_HOST) {
-        CUDA_TRY(cudaMemcpyAsync((void*)dst, ddst, dst_frame * n_frames, cudaMemcpyDeviceToHost, st));
-        cudaEventRecord(h->ev(3), st);
-    }
-    if (where == RAISR_HOST || ms) {
-        CUDA_TRY(cudaStreamSynchronize(st));
+    if (where == RAISR_DEVICE) {
+        cudaStream_t st = h->stream();
+        cudaEventRecord(h->ev(1), st);
+        for (int f = 0; f < n_frames; ++f)
+            if (int rc = enqueue_bgra_frame(h, g, src + (size_t)f * src_frame, sw, sh, src_pitch, (unsigned char*)dst + (size_t)f * dst_frame, dst_pitch,
+                                            dw, dh, scale, f32, st)) return rc;
+        cudaEventRecord(h->ev(2), st);
         if (ms) {
+            CUDA_TRY(cudaStreamSynchronize(st));
             ms[0] = ms[2] = 0;
             cudaEventElapsedTime(&ms[1], h->ev(1), h->ev(2));
-            if (where == RAISR_HOST) {
-                cudaEventElapsedTime(&ms[0], h->ev(0), h->ev(1));
-                cudaEventElapsedTime(&ms[2], h->ev(2), h->ev(3));
-            }
+        }
+        return 0;
+    }
+    // Host path: frames flow H2D -> kernels -> D2H on three streams with double-buffered frame slots
+    // (the scratch planes are shared, so the kernels of consecutive frames stay serial on one stream).
+    for (int b = 0; b < 2; ++b) {
+        if (int rc = h->dsrc[b].ensure(src_frame)) return rc;
+        if (int rc = h->ddst[b].ensure(dst_frame)) return rc;
+    }
+    cudaStream_t sc = h->own_stream, sh2d = h->h2d_stream, sd2h = h->d2h_stream;
+    // event slots per frame: 0/1 H2D, 2/3 D2H, 5/4 kernels
+    auto E = [&](int f, int k) { return h->ev(16 + (size_t)f * 8 + k); };
+    for (int f = 0; f < n_frames; ++f) {
+        const int b = f & 1;
+        if (f >= 2) CUDA_TRY(cudaStreamWaitEvent(sh2d, E(f - 2, 4), 0));   // kernels of frame f-2 are done with dsrc[b]
+        CUDA_TRY(cudaEventRecord(E(f, 0), sh2d));
+        CUDA_TRY(cudaMemcpyAsync(h->dsrc[b].p, src + (size_t)f * src_frame, src_frame, cudaMemcpyHostToDevice, sh2d));
+        CUDA_TRY(cudaEventRecord(E(f, 1), sh2d));
+        CUDA_TRY(cudaStreamWaitEvent(sc, E(f, 1), 0));
+        if (f >= 2) CUDA_TRY(cudaStreamWaitEvent(sc, E(f - 2, 3), 0));     // D2H of frame f-2 is done with ddst[b]
+        CUDA_TRY(cudaEventRecord(E(f, 5), sc));
+        if (int rc = enqueue_bgra_frame(h, g, (const uint8_t*)h->dsrc[b].p, sw, sh, src_pitch, (unsigned char*)h->ddst[b].p, dst_pitch, dw, dh, scale,
+                                        f32, sc)) return rc;
+        CUDA_TRY(cudaEventRecord(E(f, 4), sc));
+        CUDA_TRY(cudaStreamWaitEvent(sd2h, E(f, 4), 0));
+        CUDA_TRY(cudaEventRecord(E(f, 2), sd2h));
+        CUDA_TRY(cudaMemcpyAsync((unsigned char*)dst + (size_t)f * dst_frame, h->ddst[b].p, dst_frame, cudaMemcpyDeviceToHost, sd2h));
+        CUDA_TRY(cudaEventRecord(E(f, 3), sd2h));
+    }
+    CUDA_TRY(cudaStreamSynchronize(sd2h));
+    CUDA_TRY(cudaStreamSynchronize(sc));
+    CUDA_TRY(cudaStreamSynchronize(sh2d));
+    if (ms) {
+        ms[0] = ms[1] = ms[2] = 0;
+        for (int f = 0; f < n_frames; ++f) {
+            float a = 0;
+            cudaEventElapsedTime(&a, E(f, 0), E(f, 1)); ms[0] += a;
+            cudaEventElapsedTime(&a, E(f, 5), E(f, 4)); ms[1] += a;
+            cudaEventElapsedTime(&a, E(f, 2), E(f, 3)); ms[2] += a;
         }
     }
     return 0;
