@@ -154,6 +154,25 @@ class ClockSampler:
                     power_w_max=float(max(pw)), reasons=sorted(reasons), source="nvidia-smi")
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's host threads (and thereby its pinned staging buffers, first touch) to the CPUs NVML
+    lists as local to its GPU, restricted to the CPUs the container allows.  Returns a short description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(index))
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        local = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        pick = sorted(local & allowed)
+        if pick and len(pick) < len(allowed):
+            os.sched_setaffinity(0, pick)
+            return "%d of %d allowed CPUs (GPU-local)" % (len(pick), len(allowed))
+        return "no change (%d GPU-local CPUs among %d allowed)" % (len(pick), len(allowed))
+    except Exception as e:  # affinity is an optimisation, never a requirement
+        return "unavailable: %s" % type(e).__name__
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -192,6 +211,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the RAISR path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -322,7 +342,7 @@ def main():
                     clocks=clocks, gpu_launches=int(launches),
                     e2e=dict(value=round(e2e_value, 1), unit="Mpix/s", h2d_bytes_per_step=n * SW * SH, d2h_bytes_per_step=n * dw * dh,
                              h2d_kernel_d2h_ms=[round(x, 3) for x in e2e_ms3], matches_device_path=same_as_device,
-                             api="raisr_upsample_u8(where=RAISR_HOST), pinned buffers"),
+                             api="raisr_upsample_u8(where=RAISR_HOST), pinned buffers", host_affinity=numa),
                     roofline=roofline, cpu_baseline=cb)
         print(json.dumps(line), flush=True)
     r.close()
