@@ -198,6 +198,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--filter-impl", type=int, default=None, help="1 octet (default), 0 block")
     ap.add_argument("--overlap", type=int, default=None, help="1: overlapped prep/filter pipeline, 0: serial")
+    ap.add_argument("--taps", default="fp32", choices=["fp32", "fp16"],
+                    help="fp16: taps rounded to half precision like the reference's (half)pf[...] (NOT the headline configuration)")
     ap.add_argument("--chunk-mb", type=int, default=208, help="scratch budget per kernel launch in MiB (library default 208)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -219,7 +221,7 @@ def main():
     from oclcomputervision_b200 import ClRaisr, synth, _cabi
     import ctypes
     F = synth.random_filters(SCALE)
-    r = ClRaisr(1, filters=F, device=local_rank)
+    r = ClRaisr(1, filters=F, device=local_rank, taps=args.taps)
     if args.filter_impl is not None:
         r.set_option("filter_impl", args.filter_impl)
     if args.overlap is not None:
@@ -335,7 +337,7 @@ def main():
                     warmup=max(args.warmup, 3), ms_per_step=round(elapsed_ms / args.steps, 3), higher_is_better=True,
                     scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                     config=dict(workload="RAISR 2x 1080p->4K luma u8->u8, batch of %d synthetic frames per GPU, "
-                                         "random-init 24x3x3x4x121 fp32 table (BASELINE configs[1])" % n,
+                                         "random-init 24x3x3x4x121 fp32 table (BASELINE configs[1])%s" % (n, "" if args.taps == "fp32" else "; NON-DEFAULT: taps rounded to fp16 (raisr.cl:328), fp32 arithmetic"),
                                 frames_per_gpu=n, src="%dx%d" % (SW, SH), dst="%dx%d" % (dw, dh), parallelism="frames sharded, no collective",
                                 l2="per-step working set (%.0f MB in + %.0f MB out) exceeds the 126 MB L2" % (n * SW * SH / 1e6, n * dw * dh / 1e6),
                                 device=info["name"]),

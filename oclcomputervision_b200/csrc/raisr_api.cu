@@ -77,6 +77,7 @@ struct DevBuf {
 struct ScaleTable {
     DevBuf block;   // [type][bucket][132]  (filter_block_kernel)
     DevBuf octet;   // [type][bucket][128]  (filter_octet_kernel, lane-major chunks)
+    DevBuf octet16; // [type][bucket][128 halfs]  (filter_octet_kernel<H16>, only with taps_fp16)
     std::vector<float> host;  // the caller's table as given (repacked when the tap precision option changes)
     bool set = false;
 };
@@ -250,18 +251,18 @@ int make_uext_tmap(CUtensorMap* tm, const FilterParams& p, int box_rows, int box
     return 0;
 }
 
-template <int S, typename OutT, int NBUF>
+template <int S, typename OutT, int NBUF, bool H16 = false>
 int launch_filter_octet(raisr_ctx* h, FilterParams p, cudaStream_t st)
 {
     using C = OctetCfg<S>;
     using G = OctetGeom<S>;
     p.tiles_x = (p.ow + C::OTW - 1) / C::OTW;
     p.tiles_y = (p.oh + C::OTH - 1) / C::OTH;
-    size_t smem = octet_smem_bytes<S, NBUF>(p.n_buckets);
+    size_t smem = octet_smem_bytes<S, NBUF>(p.n_buckets, H16);
     if (smem > 227 * 1024) return fail(RAISR_E_UNSUPPORTED, "filter table slice of %d buckets does not fit shared memory", p.n_buckets);
     CUtensorMap tm;
     if (int rc = make_uext_tmap(&tm, p, G::PT, G::NCOLS)) return rc;
-    auto kern = filter_octet_kernel<S, OutT, NBUF>;
+    auto kern = filter_octet_kernel<S, OutT, NBUF, H16>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int ntypes = S * S;
     long long ntiles = (long long)p.tiles_x * p.tiles_y * p.n_frames;
@@ -283,6 +284,14 @@ int launch_filter(raisr_ctx* h, FilterParams p, int s, cudaStream_t st, bool sin
             case 2: return launch_filter_octet<2, OutT, 1>(h, p, st);
             case 3: return launch_filter_octet<3, OutT, 1>(h, p, st);
             case 4: return launch_filter_octet<4, OutT, 1>(h, p, st);
+            }
+        }
+        if (h->taps_fp16 && t.octet16.p) {   // fp16 records in shared memory: half the tap stream
+            p.table = (const float*)t.octet16.p;
+            switch (s) {
+            case 2: return launch_filter_octet<2, OutT, 2, true>(h, p, st);
+            case 3: return launch_filter_octet<3, OutT, 2, true>(h, p, st);
+            case 4: return launch_filter_octet<4, OutT, 2, true>(h, p, st);
             }
         }
         switch (s) {
@@ -579,7 +588,7 @@ void raisr_destroy(raisr_t* h)
     if (!h) return;
     Guard guard(h->device);
     cudaDeviceSynchronize();
-    for (auto& t : h->tables) { t.block.release(); t.octet.release(); }
+    for (auto& t : h->tables) { t.block.release(); t.octet.release(); t.octet16.release(); }
     h->uext.release(); h->hash.release(); h->dbg.release(); h->uext2.release(); h->hash2.release(); h->cplanes.release();
     if (h->prep_stream) cudaStreamDestroy(h->prep_stream);
     if (h->filt_stream) cudaStreamDestroy(h->filt_stream);
@@ -618,6 +627,15 @@ static int upload_table(raisr_ctx* h, int scale)
     if (int rc = t.block.ensure(blk.size() * sizeof(float))) return rc;
     if (int rc = t.octet.ensure(oct.size() * sizeof(float))) return rc;
     CUDA_TRY(cudaStreamSynchronize(h->stream()));   // a previous launch may still read the old table
+    if (h->taps_fp16) {
+        std::vector<uint16_t> o16((size_t)ss * nb * kOctStrideH, 0);
+        auto to_half = [](float v) { return __half_as_ushort(__float2half_rn(v)); };
+        for (int type = 0; type < ss; ++type)
+            for (int b = 0; b < nb; ++b)
+                octet_pack_filter_h16(table + ((size_t)b * ss + type) * kTaps, &o16[((size_t)type * nb + b) * kOctStrideH], scale, to_half);
+        if (int rc = t.octet16.ensure(o16.size() * sizeof(uint16_t))) return rc;
+        CUDA_TRY(cudaMemcpy(t.octet16.p, o16.data(), o16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
     CUDA_TRY(cudaMemcpy(t.block.p, blk.data(), blk.size() * sizeof(float), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(t.octet.p, oct.data(), oct.size() * sizeof(float), cudaMemcpyHostToDevice));
     t.set = true;

@@ -18,6 +18,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "raisr_filter.cuh"
@@ -59,6 +60,20 @@ inline void octet_pack_filter_s(const float* f, float* rec, int S)
     }
 }
 
+// fp16 tap records ("taps_fp16", the reference multiplies by (half)pf[...], raisr.cl:328): 128 halfs = 256 B,
+// two 16-byte chunks per lane; lane p reads chunks p and p+8, slot s of lane p is half (p + 8*(s/8))*8 + s%8.
+// `to_half` converts a float to the raw bits of its round-to-nearest fp16 value.
+constexpr int kOctStrideH = 128;   // halfs per record
+template <typename ToHalf>
+inline void octet_pack_filter_h16(const float* f, uint16_t* rec, int S, ToHalf to_half)
+{
+    float tmp[kOctStride];
+    octet_pack_filter_s(f, tmp, S);
+    for (int p = 0; p < 8; ++p)
+        for (int slot = 0; slot < 16; ++slot)
+            rec[(p + 8 * (slot / 8)) * 8 + slot % 8] = to_half(tmp[(p + 8 * (slot / 4)) * 4 + slot % 4]);
+}
+
 template <int S>
 struct OctetCfg;
 // OTW x OTH own pixels per tile, one item of IW pixels per octet, NT threads.
@@ -98,10 +113,11 @@ struct OctetGeom {
 };
 
 template <int S, int NBUF = 2>
-inline size_t octet_smem_bytes(int n_buckets)
+inline size_t octet_smem_bytes(int n_buckets, bool h16 = false)
 {
     using G = OctetGeom<S>;
-    return (size_t)n_buckets * kOctStride * sizeof(float) + NBUF * (size_t)G::BUF_BYTES + 16;   // + two mbarriers
+    const size_t rec = h16 ? kOctStrideH * 2 : kOctStride * sizeof(float);
+    return (size_t)n_buckets * rec + NBUF * (size_t)G::BUF_BYTES + 16;   // + two mbarriers
 }
 
 __device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gptr)
@@ -142,6 +158,21 @@ __device__ __forceinline__ void lds128_if(float4& t, unsigned saddr, bool pred)
         "@p ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
         : "+f"(t.x), "+f"(t.y), "+f"(t.z), "+f"(t.w)
         : "r"(saddr), "r"((unsigned)pred));
+}
+
+__device__ __forceinline__ void lds128_if(uint4& t, unsigned saddr, bool pred)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %5, 0;\n\t"
+        "@p ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+        : "+r"(t.x), "+r"(t.y), "+r"(t.z), "+r"(t.w)
+        : "r"(saddr), "r"((unsigned)pred));
+}
+// two packed halfs -> two floats (exact)
+__device__ __forceinline__ float2 h2f2(unsigned v)
+{
+    return __half22float2(*reinterpret_cast<const __half2*>(&v));
 }
 
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
@@ -193,14 +224,17 @@ __device__ __forceinline__ void octet_issue_tile(const FilterParams& p, const CU
 // NBUF = 2: the next tile is fetched while the current one is filtered.  NBUF = 1 (used when the
 // prep kernel of the next chunk shares the SM, see raisr_api.cu): one buffer, the fetch of the next
 // tile starts when the current one is done and the co-resident kernel fills the gap.
-template <int S, typename OutT, int NBUF = 2>
+// H16: the resident table holds fp16 taps (256-byte records, half the shared-memory tap stream); they are
+// widened to fp32 in registers and the arithmetic is the same fp32 FMA chain.
+template <int S, typename OutT, int NBUF = 2, bool H16 = false>
 __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const FilterParams p, const __grid_constant__ CUtensorMap tmap)
 {
     using C = OctetCfg<S>;
     using G = OctetGeom<S>;
+    constexpr int REC = H16 ? kOctStrideH * 2 : kOctStride * 4;      // bytes per filter record
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* tab = reinterpret_cast<float*>(smem_raw);                 // 512-byte records, 128-B aligned
-    unsigned char* buf0 = smem_raw + (size_t)p.n_buckets * kOctStride * sizeof(float);
+    float* tab = reinterpret_cast<float*>(smem_raw);                 // 128-B aligned records
+    unsigned char* buf0 = smem_raw + (size_t)p.n_buckets * REC;
     unsigned char* buf1 = buf0 + (NBUF - 1) * G::BUF_BYTES;
     const unsigned bar0 = (unsigned)__cvta_generic_to_shared(buf1 + G::BUF_BYTES), bar1 = bar0 + 8;
     const int tid = threadIdx.x;
@@ -226,9 +260,9 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
     if (worker < ntiles) octet_issue_tile<S>(p, &tmap, buf0, bar0, cur, type, py, px);   // in flight while the table is copied
     cp_async_commit();
     {
-        const float4* g = reinterpret_cast<const float4*>(p.table + (size_t)type * p.n_buckets * kOctStride);
+        const float4* g = reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(p.table) + (size_t)type * p.n_buckets * REC);
         float4* s = reinterpret_cast<float4*>(tab);
-        for (int i = tid; i < p.n_buckets * (kOctStride / 4); i += C::NT) s[i] = __ldg(g + i);
+        for (int i = tid; i < p.n_buckets * (REC / 16); i += C::NT) s[i] = __ldg(g + i);
     }
 
     // Lane geometry: offsets (floats) from the patch origin of the current pixel in the column-major tile.
@@ -291,8 +325,14 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
             for (int t = 0; t < G::NEWP; ++t) w5[5 - G::NEWP + t] = base[off_part[t]];
             uint2 hb = hrow[0];
             unsigned bucket = min(hb.x & 0xffu, maxb);
-            const float4* tp = tab_lane + bucket * (kOctStride / 4);
-            float4 t0 = tp[0], t1 = tp[8], t2 = tp[16], t3 = tp[24];
+            const float4* tp = tab_lane + bucket * (REC / 16);
+            float4 t0 = {}, t1 = {}, t2 = {}, t3 = {};
+            uint4 q0 = {}, q1 = {};
+            if (H16) {
+                q0 = *reinterpret_cast<const uint4*>(tp); q1 = *reinterpret_cast<const uint4*>(tp + 8);
+            } else {
+                t0 = tp[0]; t1 = tp[8]; t2 = tp[16]; t3 = tp[24];
+            }
 #pragma unroll 1
             for (int b0 = 0; b0 < C::IW; b0 += 8) {
                 if (oxs + b0 >= p.ow) break;                  // octet-uniform
@@ -306,10 +346,25 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
                     nbucket = min(nbucket, maxb);
                     const bool reload = nbucket != bucket;
                     bucket = nbucket;
-                    const unsigned tpa = tab_lane_s + nbucket * (kOctStride * 4);
+                    const unsigned tpa = tab_lane_s + nbucket * REC;
                     constexpr int MP = G::WP - 1;
                     const int o = S * b;
-                    float a0 = w11[(o + 0) % G::WF] * t0.x, a1 = w11[(o + 1) % G::WF] * t0.y;
+                    float a0, a1;
+                    if (H16) {
+                        float2 c0 = h2f2(q0.x), c1 = h2f2(q0.y), c2 = h2f2(q0.z), c3 = h2f2(q0.w);
+                        lds128_if(q0, tpa, reload);
+                        a0 = w11[(o + 0) % G::WF] * c0.x; a1 = w11[(o + 1) % G::WF] * c0.y;
+                        a0 = fmaf(w11[(o + 2) % G::WF], c1.x, a0); a1 = fmaf(w11[(o + 3) % G::WF], c1.y, a1);
+                        a0 = fmaf(w11[(o + 4) % G::WF], c2.x, a0); a1 = fmaf(w11[(o + 5) % G::WF], c2.y, a1);
+                        a0 = fmaf(w11[(o + 6) % G::WF], c3.x, a0); a1 = fmaf(w11[(o + 7) % G::WF], c3.y, a1);
+                        c0 = h2f2(q1.x); c1 = h2f2(q1.y); c2 = h2f2(q1.z); c3 = h2f2(q1.w);
+                        lds128_if(q1, tpa + 128, reload);
+                        a0 = fmaf(w11[(o + 8) % G::WF], c0.x, a0); a1 = fmaf(w11[(o + 9) % G::WF], c0.y, a1);
+                        a0 = fmaf(w11[(o + 10) % G::WF], c1.x, a0); a1 = fmaf(w5[(o + 0) & MP], c1.y, a1);
+                        a0 = fmaf(w5[(o + 1) & MP], c2.x, a0); a1 = fmaf(w5[(o + 2) & MP], c2.y, a1);
+                        a0 = fmaf(w5[(o + 3) & MP], c3.x, a0); a1 = fmaf(w5[(o + 4) & MP], c3.y, a1);
+                    } else {
+                    a0 = w11[(o + 0) % G::WF] * t0.x; a1 = w11[(o + 1) % G::WF] * t0.y;
                     a0 = fmaf(w11[(o + 2) % G::WF], t0.z, a0); a1 = fmaf(w11[(o + 3) % G::WF], t0.w, a1);
                     lds128_if(t0, tpa, reload);
                     a0 = fmaf(w11[(o + 4) % G::WF], t1.x, a0); a1 = fmaf(w11[(o + 5) % G::WF], t1.y, a1);
@@ -321,6 +376,7 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
                     a0 = fmaf(w5[(o + 1) & MP], t3.x, a0); a1 = fmaf(w5[(o + 2) & MP], t3.y, a1);
                     a0 = fmaf(w5[(o + 3) & MP], t3.z, a0); a1 = fmaf(w5[(o + 4) & MP], t3.w, a1);
                     lds128_if(t3, tpa + 384, reload);
+                    }
                     // fresh patch values of the next pixel overwrite the slots this pixel has just consumed
                     const int npix = b0 + b + 1;
                     if (npix < C::IW) {
