@@ -24,6 +24,7 @@
 #include "histeq.cuh"
 #include "raisr_color.cuh"
 #include "raisr_prep.cuh"
+#include "raisr_prep2.cuh"
 #include "raisr_resize.cuh"
 
 using namespace raisr;
@@ -104,6 +105,7 @@ struct raisr_ctx {
     long long launches = 0;
     float last_prep_ms = 0, last_filter_ms = 0;
     int filter_impl = 1;  // 0 = block (v1), 1 = octet
+    int prep_impl = 2;    // 2 = packed-fp32 prep2_kernel, 1 = scalar prep_kernel
     int as_written = 0;   // "quirks" option
     int taps_fp16 = 0;    // "taps_fp16" option
     size_t chunk_budget = 208u << 20;   // upscaled-image scratch per kernel launch: 6 frames of 1080p->4K
@@ -175,10 +177,29 @@ void launch_prep_q(PrepParams p, cudaStream_t st, int max_ctas)
     prep_kernel<S, DBG, NQ, FROM_U><<<grid, PT_THREADS, smem, st>>>(p);
 }
 
+template <int S, bool DBG, int NQ, bool FROM_U>
+void launch_prep2_q(PrepParams p, cudaStream_t st, int max_ctas)
+{
+    p.tiles_x = (p.dw + P2_W - 1) / P2_W;
+    p.tiles_y = (p.rows + P2_H - 1) / P2_H;
+    long long total = (long long)p.tiles_x * p.tiles_y * p.n_frames;
+    int grid = (int)std::max<long long>(1, std::min<long long>(total, max_ctas));
+    size_t smem = sizeof(Prep2Smem);
+    cudaFuncSetAttribute(prep2_kernel<S, DBG, NQ, FROM_U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    prep2_kernel<S, DBG, NQ, FROM_U><<<grid, P2_THREADS, smem, st>>>(p);
+}
+
+// impl 2: packed-fp32 kernel (raisr_prep2.cuh, default); impl 1: scalar kernel (raisr_prep.cuh)
 template <int S>
-void launch_prep_t(const PrepParams& p, cudaStream_t st, bool dbg, int max_ctas)
+void launch_prep_t(const PrepParams& p, cudaStream_t st, bool dbg, int max_ctas, int impl)
 {
     const bool small = p.n_strength <= 3 && p.n_coherence <= 3;   // the reference's 3 x 3 (raisr.cl:9-15)
+    if (impl == 2) {
+        if (p.uext_in) small ? launch_prep2_q<S, false, 2, true>(p, st, max_ctas) : launch_prep2_q<S, false, kMaxQ, true>(p, st, max_ctas);
+        else if (dbg) small ? launch_prep2_q<S, true, 2, false>(p, st, max_ctas) : launch_prep2_q<S, true, kMaxQ, false>(p, st, max_ctas);
+        else small ? launch_prep2_q<S, false, 2, false>(p, st, max_ctas) : launch_prep2_q<S, false, kMaxQ, false>(p, st, max_ctas);
+        return;
+    }
     if (p.uext_in) {   // colour path: hash an existing upscaled plane
         small ? launch_prep_q<S, false, 2, true>(p, st, max_ctas) : launch_prep_q<S, false, kMaxQ, true>(p, st, max_ctas);
         return;
@@ -192,9 +213,9 @@ int launch_prep(raisr_ctx* h, const PrepParams& p, int s, cudaStream_t st, bool 
 {
     const int max_ctas = ctas_per_sm > 0 ? h->sm_count * ctas_per_sm : 0x7fffffff;
     switch (s) {
-    case 2: launch_prep_t<2>(p, st, dbg, max_ctas); break;
-    case 3: launch_prep_t<3>(p, st, dbg, max_ctas); break;
-    case 4: launch_prep_t<4>(p, st, dbg, max_ctas); break;
+    case 2: launch_prep_t<2>(p, st, dbg, max_ctas, h->prep_impl); break;
+    case 3: launch_prep_t<3>(p, st, dbg, max_ctas, h->prep_impl); break;
+    case 4: launch_prep_t<4>(p, st, dbg, max_ctas, h->prep_impl); break;
     default: return fail(RAISR_E_UNSUPPORTED, "scale %d not supported (2, 3 or 4)", s);
     }
     h->launches++;
@@ -676,6 +697,7 @@ int raisr_set_option(raisr_t* h, const char* key, long long value)
     if (!h || !key) return fail(RAISR_E_ARG, "null argument");
     if (!strcmp(key, "filter_impl")) { h->filter_impl = value ? 1 : 0; return 0; }
     if (!strcmp(key, "overlap")) { h->overlap = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "prep_impl")) { h->prep_impl = value == 1 ? 1 : 2; return 0; }
     if (!strcmp(key, "quirks")) { h->as_written = value ? 1 : 0; return 0; }
     if (!strcmp(key, "taps_fp16")) {
         const int v = value ? 1 : 0;
