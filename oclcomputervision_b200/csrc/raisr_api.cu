@@ -180,13 +180,13 @@ void launch_prep_q(PrepParams p, cudaStream_t st, int max_ctas)
 template <int S, bool DBG, int NQ, bool FROM_U>
 void launch_prep2_q(PrepParams p, cudaStream_t st, int max_ctas)
 {
-    p.tiles_x = (p.dw + P2_W - 1) / P2_W;
-    p.tiles_y = (p.rows + P2_H - 1) / P2_H;
+    p.tiles_x = (p.dw + PT_W - 1) / PT_W;
+    p.tiles_y = (p.rows + PT_H - 1) / PT_H;
     long long total = (long long)p.tiles_x * p.tiles_y * p.n_frames;
     int grid = (int)std::max<long long>(1, std::min<long long>(total, max_ctas));
     size_t smem = sizeof(Prep2Smem);
     cudaFuncSetAttribute(prep2_kernel<S, DBG, NQ, FROM_U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    prep2_kernel<S, DBG, NQ, FROM_U><<<grid, P2_THREADS, smem, st>>>(p);
+    prep2_kernel<S, DBG, NQ, FROM_U><<<grid, PT_THREADS, smem, st>>>(p);
 }
 
 // impl 2: packed-fp32 kernel (raisr_prep2.cuh, default); impl 1: scalar kernel (raisr_prep.cuh)

@@ -1,17 +1,22 @@
-// raisr_prep2.cuh -- kernel A of the RAISR path, packed-fp32 version ("prep2").
+// raisr_prep2.cuh -- kernel A of the RAISR path with packed fp32 arithmetic ("prep2").
 //
-// Same contract, parameters and bit-exact results as prep_kernel (raisr_prep.cuh): bilinear upscale on
-// the extended domain (raisr.cl:48-61,198-217), Sobel as flipped convolution (:43-46,235-253), separable
-// 9-tap Gaussian structure tensor (:258-276, intended semantics), eigen-solve / quantise / hash
-// (:278-317).  What changes is how the arithmetic is issued.  prep_kernel is bound by instruction issue
-// (81 % of the slots, FMA pipe ~40 %), and on sm_100a one FFMA2 / FADD2 / FMUL2 (PTX fma/add/sub/mul
-// .rn.f32x2) does two IEEE fp32 operations for one issue slot (measured, tools/ffma2_test.cu: same
-// 72 TFLOP/s at half the issue rate).  So every stage works on PAIRS of pixels that need exactly the same
-// instruction stream: rows r and r + D of the tile (D = half the tile height).  All tile arrays in shared
-// memory hold such pairs (row n of the pair array = rows n and n + D of the tile), which keeps every
-// operand of every stage pair-aligned -- vertical neighbours r-1, r+1 of a pair are again a pair.  Each
-// lane of a pair goes through the same operations in the same order as the scalar kernel, so the results
-// are identical bit for bit.
+// Same contract, parameters, tile (64x56, 72.5 KB, three CTAs per SM) and bit-exact results as prep_kernel
+// (raisr_prep.cuh): bilinear upscale on the extended domain (raisr.cl:48-61,198-217), Sobel as flipped
+// convolution (:43-46,235-253), separable 9-tap Gaussian structure tensor (:258-276, intended semantics),
+// eigen-solve / quantise / hash (:278-317).  What changes is how the arithmetic is issued.  prep_kernel is
+// bound by instruction issue (81 % of the slots, FMA pipe ~40 %), and on sm_100a one FFMA2 / FADD2 / FMUL2
+// (PTX fma/add/sub/mul.rn.f32x2) does two IEEE fp32 operations for one issue slot (measured,
+// tools/ffma2_test.cu: the same 72 TFLOP/s at half the issue rate).  Three of the four stages are
+// therefore run on PAIRS of pixels that need exactly the same instruction stream:
+//   phase 1  (bilinear)        two vertically adjacent samples of a column
+//   phase 3a (vertical pass)   two horizontally adjacent columns (one 64-bit shared load = one pair)
+//   phase 3b (eigen / hash)    the same two columns
+// Each lane of a pair goes through the same operations in the same order as the scalar kernel, so the
+// results are identical bit for bit.  Phase 2 (Sobel + horizontal pass) stays scalar: its operands sit
+// at odd and even column offsets alike, which no pair layout serves without extra moves.
+// (A first version paired rows r and r+40 of a 64x80 tile through every stage; it needed 108 KB, ran two
+// CTAs per SM and was slower than the scalar kernel: FFMA2 holds the FMA pipe for two cycles, so a phase
+// made only of packed FMAs is pipe-bound unless CTAs in other phases fill the gaps.)
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -20,7 +25,7 @@
 
 namespace raisr {
 
-typedef unsigned long long p2;   // two packed fp32 in a 64-bit register pair: .lo = tile row r, .hi = tile row r + P2_D
+typedef unsigned long long p2;   // two packed fp32 in a 64-bit register pair (.lo, .hi)
 
 __device__ __forceinline__ p2 pk(float lo, float hi) { p2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ void upk(p2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
@@ -31,34 +36,6 @@ __device__ __forceinline__ p2 mul2(p2 a, p2 b) { p2 r; asm("mul.rn.f32x2 %0, %1,
 __device__ __forceinline__ p2 fma2(p2 a, p2 b, p2 c) { p2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 // c - a*b, one rounding (the -a*b + c step of the sqrt / divide refinements)
 __device__ __forceinline__ p2 fnma2(p2 a, p2 b, p2 c) { return fma2(mul2(a, bc(-1.0f)), b, c); }
-
-constexpr int P2_W = 64, P2_H = 80, P2_D = P2_H / 2, P2_THREADS = 256;
-constexpr int P2_UW = P2_W + 2 * kMargin;   // 74 columns of U
-constexpr int P2_UH = P2_H + 2 * kMargin;   // 90 rows of U
-constexpr int P2_NU = P2_UH - P2_D;         // 50 pair rows of U: (n, n + 40)
-constexpr int P2_UPITCH = 74;               // p2 per pair row: 37 x 16 B, odd -> 8 consecutive rows hit 8 bank groups
-constexpr int P2_HH = P2_H + 2 * kGrad;     // 88 rows of horizontally filtered products
-constexpr int P2_NH = P2_HH - P2_D;         // 48 pair rows of H: (m, m + 40)
-constexpr int P2_HPITCH = 66;               // 33 x 16 B
-constexpr int P2W_H = P2_UH / 2 + 3, P2W_W = P2_UW / 2 + 3, P2W_PITCH = P2W_W + 1;   // source window (S >= 2)
-constexpr int P2_RPT = P2_D / 4;            // 10 pair rows per thread in the vertical pass / eigen stage
-
-struct Prep2Smem {
-    p2 u[P2_NU * P2_UPITCH];
-    union {
-        p2 h[3][P2_NH * P2_HPITCH];
-        struct {
-            p2 h01[2][P2_NH * P2_HPITCH];
-            float lut[256];
-            float win[P2W_H * P2W_PITCH];
-        };
-    };
-    float colu[P2_UW];
-    float2 rowv[P2_UH];      // (v, 1-v)
-    int2 colx[P2_UW];        // window-relative x0, x1
-    int2 rowy[P2_UH];        // window-relative y0*pitch, y1*pitch
-};
-static_assert(sizeof(Prep2Smem) <= 113 * 1024 && (256 + P2W_H * P2W_PITCH) * 4 <= P2_NH * P2_HPITCH * 8, "two prep2 CTAs per SM");
 
 // sqrt_rn_guarded of both lanes (same sequence as the scalar helper, see raisr_prep.cuh)
 __device__ __forceinline__ p2 sqrt2_guarded(float xl, float xh)
@@ -71,13 +48,38 @@ __device__ __forceinline__ p2 sqrt2_guarded(float xl, float xh)
     const p2 s = mul2(x, r), h = mul2(r, bc(0.5f));
     float sl, sh;
     upk(fma2(fnma2(s, s, x), h, s), sl, sh);
-    if (!(xl >= 1.0e-30f)) sl = xl > 0.0f ? __fsqrt_rn(xl) : 0.0f;
-    if (!(xh >= 1.0e-30f)) sh = xh > 0.0f ? __fsqrt_rn(xh) : 0.0f;
+    if (!(fminf(xl, xh) >= 1.0e-30f)) {     // rare: practically only exact zeros
+        if (!(xl >= 1.0e-30f)) sl = xl > 0.0f ? __fsqrt_rn(xl) : 0.0f;
+        if (!(xh >= 1.0e-30f)) sh = xh > 0.0f ? __fsqrt_rn(xh) : 0.0f;
+    }
     return pk(sl, sh);
 }
 
+constexpr int P2_RPT = PT_H / 8;   // 7 rows per thread in the vertical pass / eigen stage (thread = 2 columns)
+constexpr int P2_D = PH_H / 2;     // 32: phases 1-2 pair tile rows r and r + 32
+constexpr int P2_NU = PU_H - P2_D; // 34 pair rows of U: (n, n + 32), n = 0..33 (rows 32, 33 appear twice)
+constexpr int P2_UPITCH = 74;      // p2 per pair row: 37 x 16 B, odd -> 8 consecutive rows hit 8 bank groups
+
+// As PrepSmem, but the upscaled tile is stored as row pairs (n, n + 32) so that phase 2 can run packed.
+struct Prep2Smem {
+    p2 u2[P2_NU * P2_UPITCH];
+    union {
+        float h[3][PH_H * PH_PITCH];
+        struct {
+            float h01[2][PH_H * PH_PITCH];
+            float lut[256];
+            float win[PW_H * PW_PITCH];
+        };
+    };
+    float colu[PU_W];
+    float2 rowv[PU_H];      // (v, 1-v)
+    int2 colx[PU_W];        // window-relative x0, x1
+    int2 rowy[PU_H];        // window-relative y0*PW_PITCH, y1*PW_PITCH
+};
+static_assert(sizeof(Prep2Smem) <= 75 * 1024, "three prep2 CTAs per SM");
+
 template <int S, bool DBG, int NQ, bool FROM_U = false>
-__global__ void __launch_bounds__(P2_THREADS, 2) prep2_kernel(const PrepParams p)
+__global__ void __launch_bounds__(PT_THREADS, 3) prep2_kernel(const PrepParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Prep2Smem& sm = *reinterpret_cast<Prep2Smem*>(smem_raw);
@@ -88,29 +90,29 @@ __global__ void __launch_bounds__(P2_THREADS, 2) prep2_kernel(const PrepParams p
     const int frame = tile / tiles_per_frame;
     const int trem = tile - frame * tiles_per_frame;
     const int by = trem / p.tiles_x, bx = trem - by * p.tiles_x;
-    const int tx0 = bx * P2_W;   // first output column of the tile
-    const int ty0 = by * P2_H;   // first band-local output row of the tile
-    const int ext_w = p.dw + 2 * kMargin, ext_h = p.rows + 2 * kMargin;
+    const int tx0 = bx * PT_W;   // first output column of the tile
+    const int ty0 = by * PT_H;   // first band-local output row of the tile
 
     if (FROM_U) {
         const float* uin = p.uext_in + (size_t)frame * p.uext_frame_stride;
-        for (int idx = tid; idx < P2_NU * P2_UW; idx += P2_THREADS) {
+        const int ext_w = p.dw + 2 * kMargin, ext_h = p.rows + 2 * kMargin;
+        for (int idx = tid; idx < P2_NU * PU_W; idx += PT_THREADS) {
             const int c = idx / P2_NU, n = idx - c * P2_NU;      // rows fastest: coalesced reads of the column-major plane
             const float* col = uin + (size_t)min(tx0 + c, ext_w - 1) * p.uext_pitch;
-            sm.u[n * P2_UPITCH + c] = pk(__ldg(col + min(ty0 + n, ext_h - 1)), __ldg(col + min(ty0 + n + P2_D, ext_h - 1)));
+            sm.u2[n * P2_UPITCH + c] = pk(__ldg(col + min(ty0 + n, ext_h - 1)), __ldg(col + min(ty0 + n + P2_D, ext_h - 1)));
         }
         __syncthreads();
     } else {
     // ---- phase 0a: texel LUT and coordinate tables (raisr.cl:209: divide, then multiply)
     sm.lut[tid] = __fdiv_rn((float)tid, 255.0f);
-    if (tid < P2_UW) {
+    if (tid < PU_W) {
         int xe = tx0 - kMargin + tid;
         float fx = __fmul_rn(__fdiv_rn((float)xe, (float)(p.dw - 1)), (float)(p.sw - 1));
         float fl = floorf(fx);
         int xi = (int)fl;
         sm.colu[tid] = __fsub_rn(fx, fl);
         sm.colx[tid] = make_int2(min(max(xi, 0), p.sw - 1), min(max(xi + 1, 0), p.sw - 1));
-    } else if (tid >= 128 && tid < 128 + P2_UH) {
+    } else if (tid >= 128 && tid < 128 + PU_H) {
         int r = tid - 128;
         int ye = p.y0 + ty0 - kMargin + r;  // global output row
         float fy = __fmul_rn(__fdiv_rn((float)ye, (float)(p.dh_glob - 1)), (float)(p.sh_glob - 1));
@@ -125,51 +127,51 @@ __global__ void __launch_bounds__(P2_THREADS, 2) prep2_kernel(const PrepParams p
     __syncthreads();
     // ---- phase 0b: make the tables window-relative (x0/y0 are monotone, so first/last bound them)
     const int wx0 = sm.colx[0].x, wy0 = sm.rowy[0].x;
-    const int ww = sm.colx[P2_UW - 1].y - wx0 + 1, wh = sm.rowy[P2_UH - 1].y - wy0 + 1;
+    const int ww = sm.colx[PU_W - 1].y - wx0 + 1, wh = sm.rowy[PU_H - 1].y - wy0 + 1;
     __syncthreads();
-    if (tid < P2_UW) {
+    if (tid < PU_W) {
         int2 c = sm.colx[tid];
         sm.colx[tid] = make_int2(c.x - wx0, c.y - wx0);
-    } else if (tid >= 128 && tid < 128 + P2_UH) {
+    } else if (tid >= 128 && tid < 128 + PU_H) {
         int2 r = sm.rowy[tid - 128];
-        sm.rowy[tid - 128] = make_int2((r.x - wy0) * P2W_PITCH, (r.y - wy0) * P2W_PITCH);
+        sm.rowy[tid - 128] = make_int2((r.x - wy0) * PW_PITCH, (r.y - wy0) * PW_PITCH);
     }
     // ---- phase 0c: source window -> float texels (read_imagef UNORM8 decode), one LUT hit per texel
     const uint8_t* src = p.src + (size_t)frame * p.src_frame_stride;
-    for (int idx = tid; idx < P2W_H * P2W_W; idx += P2_THREADS) {
-        int r = idx / P2W_W, c = idx - r * P2W_W;
-        if (r < wh && c < ww) sm.win[r * P2W_PITCH + c] = sm.lut[__ldg(src + (size_t)(wy0 + r) * p.src_pitch + wx0 + c)];
+    for (int idx = tid; idx < PW_H * PW_W; idx += PT_THREADS) {
+        int r = idx / PW_W, c = idx - r * PW_W;
+        if (r < wh && c < ww) sm.win[r * PW_PITCH + c] = sm.lut[__ldg(src + (size_t)(wy0 + r) * p.src_pitch + wx0 + c)];
     }
     __syncthreads();
 
-    // ---- phase 1: bilinear upscale of the 90x74 extended tile (raisr.cl:48-61), two rows (n, n+40) at a time.
-    // Thread = one column and a run of pair quads; a quad (4 vertically adjacent samples = 16 contiguous bytes
-    // of the column-major uext) is written with one 128-bit store by the tile that owns it.
+    // ---- phase 1: bilinear upscale of the 66x74 extended tile (raisr.cl:48-61), tile rows n and n + 32 at a
+    // time.  Thread = one column, a run of pair quads; each quad (4 vertically adjacent samples = 16 contiguous
+    // bytes of the column-major uext) is written with one 128-bit store by the tile that owns it.
+    // ptxas contracts a single-use mul.rn.f32x2 that feeds add.rn.f32x2 into FFMA2 (one rounding instead of
+    // two), so only the products are packed; the additions stay scalar, which it leaves alone.
     float* uext = p.uext + (size_t)frame * p.uext_frame_stride;
-    if (tid < 3 * P2_UW) {
-        const int c = tid % P2_UW, rg = tid / P2_UW;
+    if (tid < 3 * PU_W) {
+        const int ext_w = p.dw + 2 * kMargin, ext_h = p.rows + 2 * kMargin;
+        const int c = tid % PU_W, rg = tid / PU_W;
         const int2 cx = sm.colx[c];
         const float u = sm.colu[c], omu = __fsub_rn(1.0f, u);
         const p2 U2 = bc(u), OMU2 = bc(omu);
         const int ge = tx0 + c;  // extended-domain column
-        const bool col_owned = ge < ext_w && min(max(ge - kMargin, 0), p.dw - 1) / P2_W == bx;
+        const bool col_owned = ge < ext_w && min(max(ge - kMargin, 0), p.dw - 1) / PT_W == bx;
         const int lo = (by == 0) ? 0 : ty0 + 4;
-        const int hi = (by == p.tiles_y - 1) ? ext_h : ty0 + P2_H + 4;
-        const int q0 = rg == 0 ? 0 : (rg == 1 ? 5 : 9), q1 = rg == 0 ? 5 : (rg == 1 ? 9 : 13);   // pair quads [4q, 4q+4)
+        const int hi = (by == p.tiles_y - 1) ? ext_h : ty0 + PT_H + 4;
         float* ucol = uext + (size_t)ge * p.uext_pitch;
 #pragma unroll 1
-        for (int q = q0; q < q1; ++q) {
+        for (int q = 3 * rg; q < 3 * rg + 3; ++q) {   // pair quads: rows [4q, 4q+4) and [4q+32, 4q+36)
             float vl[4], vh[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int n = min(4 * q + k, P2_NU - 1);
-                const int2 yl = sm.rowy[n], yh = sm.rowy[n + P2_D];
-                const float2 wl = sm.rowv[n], wh2 = sm.rowv[n + P2_D];
-                const p2 p00 = pk(sm.win[yl.x + cx.x], sm.win[yh.x + cx.x]), p01 = pk(sm.win[yl.x + cx.y], sm.win[yh.x + cx.y]);
-                const p2 p10 = pk(sm.win[yl.y + cx.x], sm.win[yh.y + cx.x]), p11 = pk(sm.win[yl.y + cx.y], sm.win[yh.y + cx.y]);
-                const p2 V = pk(wl.x, wh2.x), OMV = pk(wl.y, wh2.y);
-                // ptxas contracts a single-use mul.rn.f32x2 feeding add.rn.f32x2 into FFMA2 (one rounding instead of
-                // two); the additions are therefore scalar, which it leaves alone, and only the products are packed
+                const int2 ya = sm.rowy[n], yb = sm.rowy[n + P2_D];
+                const float2 wa = sm.rowv[n], wb = sm.rowv[n + P2_D];
+                const p2 p00 = pk(sm.win[ya.x + cx.x], sm.win[yb.x + cx.x]), p01 = pk(sm.win[ya.x + cx.y], sm.win[yb.x + cx.y]);
+                const p2 p10 = pk(sm.win[ya.y + cx.x], sm.win[yb.y + cx.x]), p11 = pk(sm.win[ya.y + cx.y], sm.win[yb.y + cx.y]);
+                const p2 V = pk(wa.x, wb.x), OMV = pk(wa.y, wb.y);
                 float al, ah, tl, th;
                 upk(mul2(mul2(OMU2, OMV), p00), al, ah);
                 upk(mul2(mul2(U2, OMV), p01), tl, th);
@@ -179,21 +181,20 @@ __global__ void __launch_bounds__(P2_THREADS, 2) prep2_kernel(const PrepParams p
                 upk(mul2(mul2(U2, V), p11), tl, th);
                 al = __fadd_rn(al, tl); ah = __fadd_rn(ah, th);
                 vl[k] = al; vh[k] = ah;
-                const p2 acc = pk(al, ah);
-                if (4 * q + k < P2_NU) sm.u[n * P2_UPITCH + c] = acc;
+                if (4 * q + k < P2_NU) sm.u2[n * P2_UPITCH + c] = pk(al, ah);
             }
             if (col_owned) {
                 const int le_lo = ty0 + 4 * q, le_hi = le_lo + P2_D;   // band-local extended rows of the two quads
-                // rows 40..51 exist both as .hi of pairs 0..11 and as .lo of pairs 40..51: the .hi copy stores them
-                if (q < P2_D / 4 && le_lo >= lo && le_lo < hi) *reinterpret_cast<float4*>(ucol + le_lo) = make_float4(vl[0], vl[1], vl[2], vl[3]);
-                if (le_hi >= lo && le_hi < hi) *reinterpret_cast<float4*>(ucol + le_hi) = make_float4(vh[0], vh[1], vh[2], vh[3]);
+                // tile rows 32..35 exist both as .hi of pairs 0..3 and as .lo of pairs 32..35: the .hi copy stores them
+                const bool st_lo = q < P2_D / 4 && le_lo >= lo && le_lo < hi, st_hi = le_hi >= lo && le_hi < hi;
+                if (st_lo) *reinterpret_cast<float4*>(ucol + le_lo) = make_float4(vl[0], vl[1], vl[2], vl[3]);
+                if (st_hi) *reinterpret_cast<float4*>(ucol + le_hi) = make_float4(vh[0], vh[1], vh[2], vh[3]);
                 if (DBG && frame == 0 && p.dbg_u && ge >= kMargin && ge < p.dw + kMargin) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        if (4 * q + k >= P2_NU) continue;
                         const int a = le_lo + k, b = le_hi + k;
-                        if (q < P2_D / 4 && a >= lo && a >= kMargin && a < p.rows + kMargin) p.dbg_u[(size_t)(a - kMargin) * p.dbg_pitch + (ge - kMargin)] = vl[k];
-                        if (le_hi >= lo && le_hi < hi && b >= kMargin && b < p.rows + kMargin) p.dbg_u[(size_t)(b - kMargin) * p.dbg_pitch + (ge - kMargin)] = vh[k];
+                        if (st_lo && a >= kMargin && a < p.rows + kMargin) p.dbg_u[(size_t)(a - kMargin) * p.dbg_pitch + (ge - kMargin)] = vl[k];
+                        if (st_hi && b >= kMargin && b < p.rows + kMargin && 4 * q + k + P2_D < PU_H) p.dbg_u[(size_t)(b - kMargin) * p.dbg_pitch + (ge - kMargin)] = vh[k];
                     }
                 }
             }
@@ -202,91 +203,117 @@ __global__ void __launch_bounds__(P2_THREADS, 2) prep2_kernel(const PrepParams p
     __syncthreads();
     }
 
-    // ---- phase 2: Sobel, products, horizontal 9-tap Gaussian on pair rows.  One work item = 8 consecutive
-    // output columns of one pair row, streamed over the 16 gradient columns it needs: each new gradient
-    // column adds its term to every output that uses it, in ascending tap order (the oracle's order).
-    // Lanes of a quarter warp take 8 consecutive pair rows: conflict-free 128-bit loads and stores.
-    for (int item = tid; item < P2_NH * (P2_W / 8); item += P2_THREADS) {
-        const int q = item / P2_NH, m = item - q * P2_NH;
-        const ulonglong2* r0 = reinterpret_cast<const ulonglong2*>(&sm.u[(m + 0) * P2_UPITCH + 8 * q]);
-        const ulonglong2* r1 = reinterpret_cast<const ulonglong2*>(&sm.u[(m + 1) * P2_UPITCH + 8 * q]);
-        const ulonglong2* r2 = reinterpret_cast<const ulonglong2*>(&sm.u[(m + 2) * P2_UPITCH + 8 * q]);
-        p2 a[18], b[18], c[18];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-            ulonglong2 t = r0[i]; a[2 * i] = t.x; a[2 * i + 1] = t.y;
-            t = r1[i]; b[2 * i] = t.x; b[2 * i + 1] = t.y;
-            t = r2[i]; c[2 * i] = t.x; c[2 * i + 1] = t.y;
-        }
+    // ---- phase 2: Sobel, products, horizontal 9-tap Gaussian on row pairs (m, m + 32).  One work item = 8
+    // consecutive output columns of one pair row (256 items = one per thread), streamed over the 16 gradient
+    // columns it needs: every new gradient column adds its term to each output that uses it, which visits the
+    // taps of an output in ascending order like the oracle.  Lanes of a quarter warp take 8 consecutive pair
+    // rows, so the 128-bit loads are bank-conflict-free.
+    {
+        const int m = tid & (P2_D - 1), q = tid >> 5;
+        const ulonglong2* r0 = reinterpret_cast<const ulonglong2*>(&sm.u2[(m + 0) * P2_UPITCH + 8 * q]);
+        const ulonglong2* r1 = reinterpret_cast<const ulonglong2*>(&sm.u2[(m + 1) * P2_UPITCH + 8 * q]);
+        const ulonglong2* r2 = reinterpret_cast<const ulonglong2*>(&sm.u2[(m + 2) * P2_UPITCH + 8 * q]);
         p2 axx[8], axy[8], ayy[8];
+        p2 a0, a1, a2, b0, b1, b2, c0, c1, c2;      // columns g, g+1, g+2 of the three rows
+        { ulonglong2 t = r0[0]; a0 = t.x; a1 = t.y; t = r1[0]; b0 = t.x; b1 = t.y; t = r2[0]; c0 = t.x; c1 = t.y; }
 #pragma unroll
         for (int g = 0; g < 16; ++g) {
-            const p2 d0 = sub2(a[g], a[g + 2]), d1 = sub2(b[g], b[g + 2]), d2 = sub2(c[g], c[g + 2]);
-            const p2 gx = add2(add2(d0, add2(d1, d1)), d2);          // 2*d1 == d1+d1 exactly
-            const p2 s0 = add2(add2(a[g], add2(a[g + 1], a[g + 1])), a[g + 2]);
-            const p2 s2 = add2(add2(c[g], add2(c[g + 1], c[g + 1])), c[g + 2]);
-            const p2 gy = sub2(s0, s2);
-            const p2 pxx = mul2(gx, gx), pxy = mul2(gx, gy), pyy = mul2(gy, gy);
+            if ((g & 1) == 0) {                      // columns g+2, g+3 arrive together
+                ulonglong2 t = r0[g / 2 + 1]; a2 = t.x; const p2 a3 = t.y;
+                t = r1[g / 2 + 1]; b2 = t.x; const p2 b3 = t.y;
+                t = r2[g / 2 + 1]; c2 = t.x; const p2 c3 = t.y;
+                // even step: consume (0,1,2); the odd step that follows uses (1,2,3)
+                {
+                    const p2 d0 = sub2(a0, a2), d1 = sub2(b0, b2), d2 = sub2(c0, c2);
+                    const p2 gx = add2(add2(d0, add2(d1, d1)), d2);          // 2*d1 == d1+d1 exactly
+                    const p2 s0 = add2(add2(a0, add2(a1, a1)), a2);
+                    const p2 s2 = add2(add2(c0, add2(c1, c1)), c2);
+                    const p2 gy = sub2(s0, s2);
+                    const p2 pxx = mul2(gx, gx), pxy = mul2(gx, gy), pyy = mul2(gy, gy);
 #pragma unroll
-            for (int o = 0; o < 8; ++o) {
-                const int k = g - o;
-                if (k == 0) {
-                    axx[o] = mul2(bc(g1c(0)), pxx); axy[o] = mul2(bc(g1c(0)), pxy); ayy[o] = mul2(bc(g1c(0)), pyy);
-                } else if (k > 0 && k < 9) {
-                    axx[o] = fma2(bc(g1c(k)), pxx, axx[o]); axy[o] = fma2(bc(g1c(k)), pxy, axy[o]); ayy[o] = fma2(bc(g1c(k)), pyy, ayy[o]);
+                    for (int o = 0; o < 8; ++o) {
+                        const int k = g - o;
+                        if (k == 0) { axx[o] = mul2(bc(g1c(0)), pxx); axy[o] = mul2(bc(g1c(0)), pxy); ayy[o] = mul2(bc(g1c(0)), pyy); }
+                        else if (k > 0 && k < 9) { axx[o] = fma2(bc(g1c(k)), pxx, axx[o]); axy[o] = fma2(bc(g1c(k)), pxy, axy[o]); ayy[o] = fma2(bc(g1c(k)), pyy, ayy[o]); }
+                    }
                 }
+                {
+                    const int g1 = g + 1;
+                    const p2 d0 = sub2(a1, a3), d1 = sub2(b1, b3), d2 = sub2(c1, c3);
+                    const p2 gx = add2(add2(d0, add2(d1, d1)), d2);
+                    const p2 s0 = add2(add2(a1, add2(a2, a2)), a3);
+                    const p2 s2 = add2(add2(c1, add2(c2, c2)), c3);
+                    const p2 gy = sub2(s0, s2);
+                    const p2 pxx = mul2(gx, gx), pxy = mul2(gx, gy), pyy = mul2(gy, gy);
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        const int k = g1 - o;
+                        if (k == 0) { axx[o] = mul2(bc(g1c(0)), pxx); axy[o] = mul2(bc(g1c(0)), pxy); ayy[o] = mul2(bc(g1c(0)), pyy); }
+                        else if (k > 0 && k < 9) { axx[o] = fma2(bc(g1c(k)), pxx, axx[o]); axy[o] = fma2(bc(g1c(k)), pxy, axy[o]); ayy[o] = fma2(bc(g1c(k)), pyy, ayy[o]); }
+                    }
+                }
+                a0 = a2; a1 = a3; b0 = b2; b1 = b3; c0 = c2; c1 = c3;
             }
         }
-        ulonglong2* dxx = reinterpret_cast<ulonglong2*>(&sm.h[0][m * P2_HPITCH + 8 * q]);
-        ulonglong2* dxy = reinterpret_cast<ulonglong2*>(&sm.h[1][m * P2_HPITCH + 8 * q]);
-        ulonglong2* dyy = reinterpret_cast<ulonglong2*>(&sm.h[2][m * P2_HPITCH + 8 * q]);
+        // the H planes keep the scalar row-major layout (phase 3 pairs columns, not rows)
+        float xl[8], xh[8], yl[8], yh[8], zl[8], zh[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            dxx[i] = make_ulonglong2(axx[2 * i], axx[2 * i + 1]);
-            dxy[i] = make_ulonglong2(axy[2 * i], axy[2 * i + 1]);
-            dyy[i] = make_ulonglong2(ayy[2 * i], ayy[2 * i + 1]);
-        }
+        for (int o = 0; o < 8; ++o) { upk(axx[o], xl[o], xh[o]); upk(axy[o], yl[o], yh[o]); upk(ayy[o], zl[o], zh[o]); }
+        float4* d;
+        d = reinterpret_cast<float4*>(&sm.h[0][m * PH_PITCH + 8 * q]);           d[0] = make_float4(xl[0], xl[1], xl[2], xl[3]); d[1] = make_float4(xl[4], xl[5], xl[6], xl[7]);
+        d = reinterpret_cast<float4*>(&sm.h[0][(m + P2_D) * PH_PITCH + 8 * q]);  d[0] = make_float4(xh[0], xh[1], xh[2], xh[3]); d[1] = make_float4(xh[4], xh[5], xh[6], xh[7]);
+        d = reinterpret_cast<float4*>(&sm.h[1][m * PH_PITCH + 8 * q]);           d[0] = make_float4(yl[0], yl[1], yl[2], yl[3]); d[1] = make_float4(yl[4], yl[5], yl[6], yl[7]);
+        d = reinterpret_cast<float4*>(&sm.h[1][(m + P2_D) * PH_PITCH + 8 * q]);  d[0] = make_float4(yh[0], yh[1], yh[2], yh[3]); d[1] = make_float4(yh[4], yh[5], yh[6], yh[7]);
+        d = reinterpret_cast<float4*>(&sm.h[2][m * PH_PITCH + 8 * q]);           d[0] = make_float4(zl[0], zl[1], zl[2], zl[3]); d[1] = make_float4(zl[4], zl[5], zl[6], zl[7]);
+        d = reinterpret_cast<float4*>(&sm.h[2][(m + P2_D) * PH_PITCH + 8 * q]);  d[0] = make_float4(zh[0], zh[1], zh[2], zh[3]); d[1] = make_float4(zh[4], zh[5], zh[6], zh[7]);
     }
     __syncthreads();
 
-    // ---- phase 3a: vertical 9-tap Gaussian.  Thread = one column, 10 consecutive pair rows: per plane its
-    // 18 input pairs are pulled into registers, then (after a barrier) the 10 results overwrite the first
-    // rows of its own range in place, so phase 3b can run as a rolled loop.
-    const int xo = tid & 63, grp = tid >> 6;
+    // ---- phase 3a: vertical 9-tap Gaussian on column pairs.  Thread = two adjacent columns (one 64-bit load
+    // per row), 7 consecutive rows: per plane its 15 input pairs are pulled into registers, then (after a
+    // barrier) the 7 results overwrite the first rows of its own range in place, so phase 3b can run as a
+    // rolled loop.
+    const int xo = 2 * (tid & 31), grp = tid >> 5;
 #pragma unroll 1
     for (int ch = 0; ch < 3; ++ch) {
-        p2* plane = &sm.h[ch][(grp * P2_RPT) * P2_HPITCH + xo];
+        float* plane = &sm.h[ch][(grp * P2_RPT) * PH_PITCH + xo];
         p2 in[P2_RPT + 8];
 #pragma unroll
-        for (int k = 0; k < P2_RPT + 8; ++k) in[k] = plane[k * P2_HPITCH];
+        for (int k = 0; k < P2_RPT + 8; ++k) in[k] = *reinterpret_cast<const p2*>(plane + k * PH_PITCH);
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < P2_RPT; ++j) {
             p2 mm = mul2(bc(g1c(0)), in[j]);
 #pragma unroll
             for (int k = 1; k < 9; ++k) mm = fma2(bc(g1c(k)), in[j + k], mm);
-            plane[j * P2_HPITCH] = mm;
+            *reinterpret_cast<p2*>(plane + j * PH_PITCH) = mm;
         }
     }
     // no barrier needed: phase 3b reads back only what this thread wrote
 
-    // ---- phase 3b: 2x2 eigen-solve, quantise, hash (raisr.cl:278-317), both rows of a pair at once
+    // ---- phase 3b: 2x2 eigen-solve, quantise, hash (raisr.cl:278-317) for the two columns of the thread
     {
-        const int x = tx0 + xo;
+        const int x = tx0 + xo;                 // .lo column; .hi is x + 1
         const float PI_F = 3.14159265358979323846f;
         float sq[NQ], cq[NQ];
 #pragma unroll
         for (int i = 0; i < NQ; ++i) { sq[i] = p.sq[i]; cq[i] = p.cq[i]; }
-        const int xs = x / S, xt = x % S;
-        const bool col_ok = x < p.dw;
-        uint8_t* hbase = p.hash + (size_t)frame * p.hash_frame_stride + xs;
-        const p2* hp = &sm.h[0][(grp * P2_RPT) * P2_HPITCH + xo];
+        const int xsl = x / S, xtl = x % S, xsh = (x + 1) / S, xth = (x + 1) % S;
+        const bool okl = x < p.dw, okh = x + 1 < p.dw;
+        // per-thread store cursor: pixel row-type alternates with the row, own row advances every S rows
+        const int yl0 = ty0 + grp * P2_RPT;
+        int yt = yl0 % S;                  // y0 is a multiple of S, so yl % S == global y % S
+        const size_t row_step = (size_t)S * p.hash_plane_stride;                       // next row: next row-type
+        const size_t wrap_step = p.hash_pitch - (size_t)(S - 1) * row_step;            // after S rows: first row-type, next own row
+        uint8_t* hrow = p.hash + (size_t)frame * p.hash_frame_stride + (size_t)(yt * S) * p.hash_plane_stride + (size_t)(yl0 / S) * p.hash_pitch;
+        const size_t offl = (size_t)xtl * p.hash_plane_stride + xsl, offh = (size_t)xth * p.hash_plane_stride + xsh;
+        const float* hp = &sm.h[0][(grp * P2_RPT) * PH_PITCH + xo];
 #pragma unroll 1
         for (int j = 0; j < P2_RPT; ++j) {
-            const p2 mb = hp[P2_NH * P2_HPITCH];
-            const p2 ma = p.as_written ? mb : hp[0];            // raisr.cl:271 accumulates gx*gy into ma
-            const p2 md = hp[2 * P2_NH * P2_HPITCH];
-            hp += P2_HPITCH;
+            const p2 mb = *reinterpret_cast<const p2*>(hp + PH_H * PH_PITCH);
+            const p2 ma = p.as_written ? mb : *reinterpret_cast<const p2*>(hp);            // raisr.cl:271 accumulates gx*gy into ma
+            const p2 md = *reinterpret_cast<const p2*>(hp + 2 * PH_H * PH_PITCH);
+            hp += PH_PITCH;
             const p2 T = add2(ma, md);
             float dal, dah, dbl, dbh;                       // scalar subtraction: see the note on contraction in phase 1
             upk(mul2(ma, md), dal, dah);
@@ -349,8 +376,10 @@ __global__ void __launch_bounds__(P2_THREADS, 2) prep2_kernel(const PrepParams p
                 r = fma2(r, fnma2(den, r, bc(1.0f)), r);
                 const p2 qq = mul2(num, r);
                 upk(fma2(r, fnma2(den, qq, num), qq), col, coh);
-                if (!(dl >= 1.0e-15f && dl <= 1.0e15f)) col = dl != 0.0f ? __fdiv_rn(nl, dl) : 0.0f;
-                if (!(dh >= 1.0e-15f && dh <= 1.0e15f)) coh = dh != 0.0f ? __fdiv_rn(nh, dh) : 0.0f;
+                if (!(fminf(dl, dh) >= 1.0e-15f && fmaxf(dl, dh) <= 1.0e15f)) {
+                    if (!(dl >= 1.0e-15f && dl <= 1.0e15f)) col = dl != 0.0f ? __fdiv_rn(nl, dl) : 0.0f;
+                    if (!(dh >= 1.0e-15f && dh <= 1.0e15f)) coh = dh != 0.0f ? __fdiv_rn(nh, dh) : 0.0f;
+                }
             }
             // theta / pi with the divide's own fast path (theta is 0 or in [1e-8, pi]; exact for theta = 0)
             float tql, tqh;
@@ -378,31 +407,27 @@ __global__ void __launch_bounds__(P2_THREADS, 2) prep2_kernel(const PrepParams p
             if (p.as_written) sil = sih = 0;                         // raisr.cl:316 leaves strength out of the hash
             const int bl = (al * p.n_strength + sil) * p.n_coherence + cil;
             const int bh = (ah * p.n_strength + sih) * p.n_coherence + cih;
-            const int yl_lo = ty0 + grp * P2_RPT + j, yl_hi = yl_lo + P2_D;   // band-local output rows
-            if (col_ok) {
-                if (yl_lo < p.rows) {
-                    const int type = (yl_lo % S) * S + xt;
-                    hbase[(size_t)type * p.hash_plane_stride + (size_t)(yl_lo / S) * p.hash_pitch] = (uint8_t)bl;
-                    if (DBG && frame == 0) {
-                        const size_t o = (size_t)yl_lo * p.dbg_pitch + x;
-                        if (p.dbg_hash) p.dbg_hash[o] = bl * (S * S) + type;
+            const int yl = yl0 + j;  // band-local output row
+            if (yl < p.rows) {
+                if (okl) hrow[offl] = (uint8_t)bl;
+                if (okh) hrow[offh] = (uint8_t)bh;
+                if (DBG && frame == 0) {
+                    const size_t o = (size_t)yl * p.dbg_pitch + x;
+                    if (okl) {
+                        if (p.dbg_hash) p.dbg_hash[o] = bl * (S * S) + yt * S + xtl;
                         if (p.dbg_angle) p.dbg_angle[o] = thl;
                         if (p.dbg_l1) p.dbg_l1[o] = L1l;
                         if (p.dbg_coh) p.dbg_coh[o] = col;
                     }
-                }
-                if (yl_hi < p.rows) {
-                    const int type = (yl_hi % S) * S + xt;
-                    hbase[(size_t)type * p.hash_plane_stride + (size_t)(yl_hi / S) * p.hash_pitch] = (uint8_t)bh;
-                    if (DBG && frame == 0) {
-                        const size_t o = (size_t)yl_hi * p.dbg_pitch + x;
-                        if (p.dbg_hash) p.dbg_hash[o] = bh * (S * S) + type;
-                        if (p.dbg_angle) p.dbg_angle[o] = thh;
-                        if (p.dbg_l1) p.dbg_l1[o] = L1h;
-                        if (p.dbg_coh) p.dbg_coh[o] = coh;
+                    if (okh) {
+                        if (p.dbg_hash) p.dbg_hash[o + 1] = bh * (S * S) + yt * S + xth;
+                        if (p.dbg_angle) p.dbg_angle[o + 1] = thh;
+                        if (p.dbg_l1) p.dbg_l1[o + 1] = L1h;
+                        if (p.dbg_coh) p.dbg_coh[o + 1] = coh;
                     }
                 }
             }
+            if (++yt == S) { yt = 0; hrow += wrap_step; } else hrow += row_step;
         }
     }
     __syncthreads();   // shared memory is reused by the next tile
