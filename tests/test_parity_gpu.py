@@ -258,3 +258,32 @@ def test_quirks_and_fp16_taps_against_oracle(quirks, taps, scale):
     r.set_option("taps_fp16", 0)
     r.set_option("quirks", 0)
     assert np.abs(r.upsample_f32(src, scale) - base["out_f32"])[r.debug_hash(src, scale)[0] == base["hash"]].max() <= 1e-4
+
+
+# ---------------------------------------------------------------- degenerate shapes
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(1, 1), (1, 7), (5, 1), (2, 2), (3, 200), (200, 3), (1, 300), (63, 65)])
+@pytest.mark.parametrize("s", [2, 3, 4])
+def test_tiny_and_sliver_shapes(shape, s):
+    """Sources of one row / one column / one pixel: every clamp of the bilinear map, the tile halo and the
+    TMA box is exercised at once.  Both prep kernels must agree with the oracle and with each other."""
+    src = synth.synthetic_frame(max(shape[0], 8), max(shape[1], 8), seed=17)[:shape[0], :shape[1]].copy()
+    flt = synth.random_filters(s, seed=4)
+    want = O.raisr_ref_c(src, flt, s)
+    outs = []
+    for prep_impl in (2, 1):
+        r = ClRaisr(1, device=0)
+        setattr(r, "filters_x%d" % s, flt)
+        r.set_option("prep_impl", prep_impl)
+        h, ang, l1, coh, u = r.debug_hash(src, s)
+        assert np.array_equal(u, want["U"]) and np.array_equal(l1, want["L1"]) and np.array_equal(coh, want["coherence"])
+        bad = h != want["hash"]
+        assert not (bad & ~(O.edge_distance(want) < 1e-5)).any()
+        out = r.upsample_f32(src, s)
+        assert np.abs(out - want["out_f32"])[~bad].max() <= 1e-4
+        dst = np.empty((shape[0] * s, shape[1] * s), np.uint8)
+        r.upsample(src, dst, s)
+        assert np.abs(dst.astype(int) - want["out_u8"].astype(int))[~bad].max() <= 1
+        outs.append((h, out, dst))
+        r.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
