@@ -174,13 +174,41 @@ def bind_to_gpu_numa_node(index):
 
 
 def run_reference(args, rank, world):
+    """Reference arm: the reference has no CPU RAISR path and its OpenCL kernel cannot run here, so this times the
+    oracle's C port of raisr.cl on all host threads.  One step = a bounded sample of the bench workload (as many
+    1080p->4K frames as fit ~2 s); W warm-up steps, K timed steps."""
     if rank != 0:
         return
-    cb = cpu_baseline(budget_s=max(4.0, 4.0 * args.steps))
+    from oracle import raisr_oracle as O
+    from oclcomputervision_b200 import synth
+    F = synth.random_filters(SCALE)
+    frame = synth.synthetic_frame(SH, SW, 1000)
+    threads = len(os.sched_getaffinity(0))
+    t0 = time.perf_counter()
+    O.raisr_ref_c(frame, F, SCALE, nthreads=threads, want=("out_u8",))
+    one = time.perf_counter() - t0
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    step_budget = min(2.0, 150.0 / (steps + warm))
+    n = int(max(1, min(64, step_budget / max(one, 1e-3))))
+
+    def step():
+        for _ in range(n):
+            O.raisr_ref_c(frame, F, SCALE, nthreads=threads, want=("out_u8",))
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    mpix = steps * n * SW * SH * SCALE * SCALE / dt / 1e6
+    cb = dict(value=round(mpix, 3), unit="Mpix/s", cores=threads, kind="port",
+              sample="%d step(s) of %d frame(s) of the %dx%d->%dx%d workload, C oracle (fp32, OpenMP), %.1f s" %
+                     (steps, n, SW, SH, SW * SCALE, SH * SCALE, dt))
     line = dict(metric="RAISR 2x output Mpix/s", value=cb["value"], unit="Mpix/s", impl="reference",
-                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=None,
+                n_gpus=args.gpus, steps=steps, warmup=warm, ms_per_step=round(dt / steps * 1e3, 3),
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload="RAISR 2x 1080p->4K luma, random-init 24x3x3x4x121 table (BASELINE configs[1])",
+                config=dict(workload="RAISR 2x 1080p->4K luma u8->u8, random-init 24x3x3x4x121 fp32 table (BASELINE configs[1]); "
+                                     "bounded sample: %d frame(s) per step" % n,
                             note="the reference has no CPU RAISR path and its OpenCL kernel cannot run here; "
                                  "this is the oracle's C port of raisr.cl on the host cores"),
                 cpu_baseline=cb, gpu_launches=0,
