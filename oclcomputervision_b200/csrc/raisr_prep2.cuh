@@ -138,9 +138,13 @@ __global__ void __launch_bounds__(PT_THREADS, 3) prep2_kernel(const PrepParams p
     }
     // ---- phase 0c: source window -> float texels (read_imagef UNORM8 decode), one LUT hit per texel
     const uint8_t* src = p.src + (size_t)frame * p.src_frame_stride;
-    for (int idx = tid; idx < PW_H * PW_W; idx += PT_THREADS) {
-        int r = idx / PW_W, c = idx - r * PW_W;
-        if (r < wh && c < ww) sm.win[r * PW_PITCH + c] = sm.lut[__ldg(src + (size_t)(wy0 + r) * p.src_pitch + wx0 + c)];
+    {   // 64 threads per window row (ww <= PW_W = 40 of them active), four rows per pass: no index division
+        const int c = tid & 63;
+        if (c < ww) {
+            const uint8_t* sp = src + (size_t)(wy0 + (tid >> 6)) * p.src_pitch + wx0 + c;
+            float* wp = &sm.win[(tid >> 6) * PW_PITCH + c];
+            for (int r = tid >> 6; r < wh; r += 4, sp += 4 * p.src_pitch, wp += 4 * PW_PITCH) *wp = sm.lut[__ldg(sp)];
+        }
     }
     __syncthreads();
 
