@@ -184,6 +184,11 @@ int raisr_dev_free(raisr_t* h, void* p);
 /* Pinned host memory for the HOST path (stands in for mem_flags.USE_HOST_PTR, raisr.py:99-115). */
 int raisr_host_alloc(void** p, size_t bytes);
 int raisr_host_free(void* p);
+/* Page-lock memory the caller already owns (e.g. the numpy arrays a reference-style loop passes to
+ * upsample() again and again, raisr.py:166-182) so that the HOST path copies at full PCIe speed.
+ * The range must be unregistered before it is freed. */
+int raisr_host_register(void* p, size_t bytes);
+int raisr_host_unregister(void* p);
 
 /* Block until all work enqueued by this handle is complete. */
 int raisr_sync(raisr_t* h);

@@ -52,6 +52,8 @@ SIGNATURES = {
     "raisr_dev_alloc": (c_int, [c_void_p, POINTER(c_void_p), c_size_t]),
     "raisr_dev_free": (c_int, [c_void_p, c_void_p]),
     "raisr_host_alloc": (c_int, [POINTER(c_void_p), c_size_t]),
+    "raisr_host_register": (c_int, [c_void_p, c_size_t]),
+    "raisr_host_unregister": (c_int, [c_void_p]),
     "raisr_host_free": (c_int, [c_void_p]),
     "raisr_sync": (c_int, [c_void_p]),
     "raisr_launch_count": (c_longlong, [c_void_p]),

@@ -1237,6 +1237,20 @@ int raisr_host_free(void* p)
     return 0;
 }
 
+int raisr_host_register(void* p, size_t bytes)
+{
+    if (!p || !bytes) return fail(RAISR_E_ARG, "null argument");
+    CUDA_TRY(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return 0;
+}
+
+int raisr_host_unregister(void* p)
+{
+    if (!p) return 0;
+    CUDA_TRY(cudaHostUnregister(p));
+    return 0;
+}
+
 int raisr_sync(raisr_t* h)
 {
     if (!h) return fail(RAISR_E_ARG, "null handle");

@@ -21,6 +21,7 @@ from __future__ import annotations
 import ctypes
 import os
 import pickle
+import weakref
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -235,6 +236,47 @@ class ClRaisr:
         if src.strides[-1] != 1 or dst.strides[-1] != 1 or (channels > 1 and (src.strides[1] != channels or dst.strides[1] != channels)):
             raise ValueError("rows must be contiguous")
         return src, dst
+
+    # ---- page-locking of caller-owned arrays (no reference counterpart; see raisr_host_register)
+    _pinned = {}
+
+    @classmethod
+    def pin(cls, arr: np.ndarray) -> np.ndarray:
+        """Page-lock the memory of a C-contiguous numpy array that will be passed to `upsample` repeatedly (the
+        reference's own loop, raisr.py:166-182, re-uses one src and one dst): the HOST path then copies at full
+        PCIe speed instead of through the driver's pageable staging.  The lock is released when the array is
+        garbage-collected or `unpin` is called.  Returns `arr`."""
+        if not isinstance(arr, np.ndarray) or not arr.flags.c_contiguous or arr.nbytes == 0:
+            raise ValueError("pin() needs a non-empty C-contiguous numpy array")
+        key = arr.ctypes.data
+        if key in cls._pinned:
+            return arr
+        lib = _cabi.load()
+        _cabi.check(lib.raisr_host_register(key, arr.nbytes))
+        owner = arr if arr.base is None else arr.base
+        fin = None
+        try:
+            fin = weakref.finalize(owner, cls._unregister, key)
+        except TypeError:       # the owner of the memory is not weak-referenceable: the caller must unpin
+            pass
+        cls._pinned[key] = fin
+        return arr
+
+    @classmethod
+    def _unregister(cls, key: int) -> None:
+        if cls._pinned.pop(key, "absent") != "absent":
+            try:
+                _cabi.load().raisr_host_unregister(key)
+            except Exception:
+                pass
+
+    @classmethod
+    def unpin(cls, arr: np.ndarray) -> None:
+        key = arr.ctypes.data
+        fin = cls._pinned.get(key)
+        if fin is not None:
+            fin.detach()
+        cls._unregister(key)
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:

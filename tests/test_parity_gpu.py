@@ -287,3 +287,31 @@ def test_tiny_and_sliver_shapes(shape, s):
         outs.append((h, out, dst))
         r.close()
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
+
+
+@pytest.mark.gpu
+def test_pinned_caller_arrays_same_result_and_released():
+    """`ClRaisr.pin` page-locks caller-owned arrays for a reference-style loop; results are unchanged and the lock
+    goes away with the array (or on unpin)."""
+    import gc
+    s = 2
+    src = synth.synthetic_frame(270, 480, seed=8)
+    flt = synth.random_filters(s, seed=6)
+    r = ClRaisr(1, filters=flt, device=0)
+    dst0 = np.empty((540, 960), np.uint8)
+    r.upsample(src, dst0, s)
+    psrc, pdst = ClRaisr.pin(src.copy()), ClRaisr.pin(np.empty((540, 960), np.uint8))
+    assert ClRaisr.pin(psrc) is psrc                      # idempotent
+    for _ in range(3):
+        ms = r.upsample(psrc, pdst, s)
+    assert np.array_equal(pdst, dst0) and len(ms) == 3
+    key = pdst.ctypes.data
+    assert key in ClRaisr._pinned
+    ClRaisr.unpin(psrc)
+    assert psrc.ctypes.data not in ClRaisr._pinned
+    del pdst
+    gc.collect()
+    assert key not in ClRaisr._pinned
+    with pytest.raises(ValueError):
+        ClRaisr.pin(np.empty((4, 4), np.uint8)[:, ::2])
+    r.close()
