@@ -20,6 +20,7 @@
 
 #include "raisr_filter.cuh"
 #include "raisr_octet.cuh"
+#include "raisr_octet2.cuh"
 #include <cuda_fp16.h>
 #include "histeq.cuh"
 #include "raisr_color.cuh"
@@ -106,6 +107,7 @@ struct raisr_ctx {
     float last_prep_ms = 0, last_filter_ms = 0;
     int filter_impl = 1;  // 0 = block (v1), 1 = octet
     int prep_impl = 2;    // 2 = packed-fp32 prep2_kernel, 1 = scalar prep_kernel
+    int color_filter_impl = 2;  // 2 = two planes per CTA (s = 2, fp32 taps), 1 = one launch per plane
     int as_written = 0;   // "quirks" option
     int taps_fp16 = 0;    // "taps_fp16" option
     size_t chunk_budget = 208u << 20;   // upscaled-image scratch per kernel launch: 6 frames of 1080p->4K
@@ -289,6 +291,31 @@ int launch_filter_octet(raisr_ctx* h, FilterParams p, cudaStream_t st)
     long long ntiles = (long long)p.tiles_x * p.tiles_y * p.n_frames;
     int workers = (int)std::max<long long>(1, std::min<long long>(h->sm_count / ntypes, ntiles));
     kern<<<workers * ntypes, C::NT, smem, st>>>(p, tm);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// Colour path, s = 2, fp32 taps: all four planes in one launch, two planes per CTA (raisr_octet2.cuh).
+// `p.uext` / `p.dst` point at plane 0, the frame strides are the plane strides.
+int launch_filter_octet2(raisr_ctx* h, FilterParams p, cudaStream_t st)
+{
+    using C = Octet2Cfg;
+    using G = Octet2Geom;
+    p.tiles_x = (p.ow + C::OTW - 1) / C::OTW;
+    p.tiles_y = (p.oh + C::OTH - 1) / C::OTH;
+    p.table = (const float*)h->tables[2].octet.p;
+    const size_t smem = octet2_smem_bytes(p.n_buckets);
+    if (smem > 227 * 1024) return 1;    // does not fit: the caller falls back to one launch per plane
+    FilterParams tp = p;
+    tp.n_frames = 4;                     // the tensor map's third dimension walks the planes
+    CUtensorMap tm;
+    if (int rc = make_uext_tmap(&tm, tp, G::PT, G::NCOLS)) return rc;
+    CUDA_TRY(cudaFuncSetAttribute(filter_octet2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntypes = 4;
+    const long long ntiles = (long long)p.tiles_x * p.tiles_y;
+    const int workers = (int)std::max<long long>(1, std::min<long long>(h->sm_count / (2 * ntypes), ntiles));
+    filter_octet2_kernel<<<dim3(workers * ntypes, 2), C::NT, smem, st>>>(p, tm);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -698,6 +725,7 @@ int raisr_set_option(raisr_t* h, const char* key, long long value)
     if (!strcmp(key, "filter_impl")) { h->filter_impl = value ? 1 : 0; return 0; }
     if (!strcmp(key, "overlap")) { h->overlap = value ? 1 : 0; return 0; }
     if (!strcmp(key, "prep_impl")) { h->prep_impl = value == 1 ? 1 : 2; return 0; }
+    if (!strcmp(key, "color_filter_impl")) { h->color_filter_impl = value == 1 ? 1 : 2; return 0; }
     if (!strcmp(key, "quirks")) { h->as_written = value ? 1 : 0; return 0; }
     if (!strcmp(key, "taps_fp16")) {
         const int v = value ? 1 : 0;
@@ -788,10 +816,20 @@ static int enqueue_bgra_frame(raisr_ctx* h, const Geometry& g, const uint8_t* ds
     fill_params(h, g, dsrc, sw, sh, src_pitch, h->cplanes.p, fpitch * sizeof(float), scale, 0, 1, (float*)h->uext.p, (uint8_t*)h->hash.p, pp, fp);
     pp.uext_in = (const float*)h->uext.p;   // Y plane
     if (int rc = launch_prep(h, pp, scale, st, false)) return rc;
-    for (int k = 0; k < 4; ++k) {
+    fp.raw_f32 = 1;
+    bool done = false;
+    if (scale == 2 && !h->taps_fp16 && h->color_filter_impl == 2) {   // two planes per CTA, one launch
+        fp.uext = (const float*)h->uext.p;
+        fp.uext_frame_stride = g.uext_frame;
+        fp.dst = h->cplanes.p;
+        fp.dst_frame_stride = fplane * sizeof(float);
+        const int rc = launch_filter_octet2(h, fp, st);
+        if (rc < 0) return rc;
+        done = rc == 0;
+    }
+    for (int k = 0; k < 4 && !done; ++k) {
         fp.uext = (const float*)h->uext.p + g.uext_frame * k;
         fp.dst = (float*)h->cplanes.p + fplane * k;
-        fp.raw_f32 = 1;
         if (int rc = launch_filter<float>(h, fp, scale, st)) return rc;
     }
     ColorPackParams cp{};
