@@ -24,15 +24,24 @@ struct HistParams {
     int tiles_x, tiles_y;
 };
 
-// One CTA per tile.  The counting rate is set by the shared-memory atomic unit (about 7 updates/clk/SM
-// on uniformly random bytes, 32 clk per warp-instruction when all lanes hit one bin), so equal bytes are
-// merged before they reach it: a 16-byte chunk of one value costs one atomic instead of sixteen, which
-// keeps flat regions (sky, saturation) as fast as noise.
+// One CTA per tile.  The counting rate is set by the shared-memory atomic unit, and with one 256-entry
+// histogram per warp most of its time goes to bank collisions of unrelated bins (bank = bin % 32: 3.7
+// wavefronts per warp-atomic on random bytes).  The CTA therefore keeps 16 interleaved copies,
+// counter (bin, lane % 16) at word bin*16 + lane%16, so the bank of an update is 16*(bin & 1) + lane%16:
+// only lanes l and l+16 can collide (~1.5 wavefronts per warp-atomic), and the 16-copy fold per tile costs
+// less than it saves.  Equal bytes are merged before they reach the atomic unit: a 16-byte chunk of one
+// value costs one atomic instead of sixteen, which keeps flat regions (sky, saturation) as fast as noise.
+constexpr int kHistCopies = 16;
+
 __global__ void __launch_bounds__(256) hist_tiles_kernel(const HistParams p)
 {
-    __shared__ uint32_t sh[8][kHistBins];
-    const int tid = threadIdx.x, warp = tid >> 5;
-    for (int i = tid; i < 8 * kHistBins; i += 256) (&sh[0][0])[i] = 0;
+    __shared__ __align__(16) uint32_t sh[kHistBins * kHistCopies];   // 16 KB
+    const int tid = threadIdx.x;
+    {
+        uint4* z = reinterpret_cast<uint4*>(sh);
+#pragma unroll
+        for (int i = 0; i < kHistBins * kHistCopies / 4 / 256; ++i) z[tid + 256 * i] = make_uint4(0, 0, 0, 0);
+    }
     __syncthreads();
     const int tx = blockIdx.x, ty = blockIdx.y;
     // 256 x 32 bytes = 512 chunks of 16 bytes; thread t takes chunks t and t+256 (rows t/16 and 16+t/16)
@@ -53,29 +62,35 @@ __global__ void __launch_bounds__(256) hist_tiles_kernel(const HistParams p)
                           ((uint32_t)__ldg(src + 4 * i + 2) << 16) | ((uint32_t)__ldg(src + 4 * i + 3) << 24);
         }
     }
-    uint32_t* mine = sh[warp];
+    uint32_t* mine = sh + (tid & (kHistCopies - 1));
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const uint32_t w0 = w[k][0];
         if (w0 == __byte_perm(w0, 0, 0) && w[k][1] == w0 && w[k][2] == w0 && w[k][3] == w0) {
-            atomicAdd(mine + (w0 & 0xffu), 16u);
+            atomicAdd(mine + (w0 & 0xffu) * kHistCopies, 16u);
             continue;
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const uint32_t v = w[k][i];
             if (v == __byte_perm(v, 0, 0)) {
-                atomicAdd(mine + (v & 0xffu), 4u);
+                atomicAdd(mine + (v & 0xffu) * kHistCopies, 4u);
             } else {
 #pragma unroll
-                for (int b = 0; b < 4; ++b) atomicAdd(mine + ((v >> (8 * b)) & 0xffu), 1u);
+                for (int b = 0; b < 4; ++b) atomicAdd(mine + ((v >> (8 * b)) & 0xffu) * kHistCopies, 1u);
             }
         }
     }
     __syncthreads();
+    // fold: thread = bin; its 16 copies are 64 contiguous bytes, read as four 16-byte pieces starting at a
+    // lane-dependent piece so that the eight lanes of a quarter warp touch different bank groups
+    const uint4* row = reinterpret_cast<const uint4*>(sh + tid * kHistCopies);
     uint32_t acc = 0;
 #pragma unroll
-    for (int wgt = 0; wgt < 8; ++wgt) acc += sh[wgt][tid];
+    for (int i = 0; i < 4; ++i) {
+        const uint4 v = row[(i + (tid >> 1)) & 3];
+        acc += v.x + v.y + v.z + v.w;
+    }
     p.hist[((size_t)ty * p.tiles_x + tx) * kHistBins + tid] = acc;
 }
 
