@@ -73,6 +73,8 @@ int raisr_set_stream(raisr_t* h, void* cuda_stream);
  *   "quirks"    1 = "as written": the three slips of the shipped kernel text are reproduced --
  *               ma accumulates gx*gy (raisr.cl:271), the coherence bucket compares L1 (raisr.cl:310),
  *               strength is left out of the hash (raisr.cl:316)
+ *   "cheap_upscaler" 1 = stage 1 uses the reference's cubic_sample (raisr.cl:63-106, present in the kernel
+ *               source but never called) instead of linear_sample; gray path only
  *   "taps_fp16" 1 = every tap is rounded to fp16 before use, as the reference's `(half)pf[...]`
  *               (raisr.cl:328) does; arithmetic stays fp32.  Re-packs the tables already set. */
 int raisr_set_option(raisr_t* h, const char* key, long long value);

@@ -108,6 +108,7 @@ struct raisr_ctx {
     int filter_impl = 1;  // 0 = block (v1), 1 = octet
     int prep_impl = 2;    // 2 = packed-fp32 prep2_kernel, 1 = scalar prep_kernel
     int color_filter_impl = 2;  // 2 = two planes per CTA (s = 2, fp32 taps), 1 = one launch per plane
+    int cubic = 0;        // "cheap_upscaler" option: 1 = bicubic stage 1 (gray path, prep2 kernel)
     int as_written = 0;   // "quirks" option
     int taps_fp16 = 0;    // "taps_fp16" option
     size_t chunk_budget = 208u << 20;   // upscaled-image scratch per kernel launch: 6 frames of 1080p->4K
@@ -179,7 +180,7 @@ void launch_prep_q(PrepParams p, cudaStream_t st, int max_ctas)
     prep_kernel<S, DBG, NQ, FROM_U><<<grid, PT_THREADS, smem, st>>>(p);
 }
 
-template <int S, bool DBG, int NQ, bool FROM_U>
+template <int S, bool DBG, int NQ, bool FROM_U, bool CUBIC = false>
 void launch_prep2_q(PrepParams p, cudaStream_t st, int max_ctas)
 {
     p.tiles_x = (p.dw + PT_W - 1) / PT_W;
@@ -187,8 +188,8 @@ void launch_prep2_q(PrepParams p, cudaStream_t st, int max_ctas)
     long long total = (long long)p.tiles_x * p.tiles_y * p.n_frames;
     int grid = (int)std::max<long long>(1, std::min<long long>(total, max_ctas));
     size_t smem = sizeof(Prep2Smem);
-    cudaFuncSetAttribute(prep2_kernel<S, DBG, NQ, FROM_U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    prep2_kernel<S, DBG, NQ, FROM_U><<<grid, PT_THREADS, smem, st>>>(p);
+    cudaFuncSetAttribute(prep2_kernel<S, DBG, NQ, FROM_U, CUBIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    prep2_kernel<S, DBG, NQ, FROM_U, CUBIC><<<grid, PT_THREADS, smem, st>>>(p);
 }
 
 // impl 2: packed-fp32 kernel (raisr_prep2.cuh, default); impl 1: scalar kernel (raisr_prep.cuh)
@@ -197,6 +198,10 @@ void launch_prep_t(const PrepParams& p, cudaStream_t st, bool dbg, int max_ctas,
 {
     const bool small = p.n_strength <= 3 && p.n_coherence <= 3;   // the reference's 3 x 3 (raisr.cl:9-15)
     if (impl == 2) {
+        if (p.cubic) {   // optional stage-1 variant: the general-quantiser instantiation only
+            dbg ? launch_prep2_q<S, true, kMaxQ, false, true>(p, st, max_ctas) : launch_prep2_q<S, false, kMaxQ, false, true>(p, st, max_ctas);
+            return;
+        }
         if (p.uext_in) small ? launch_prep2_q<S, false, 2, true>(p, st, max_ctas) : launch_prep2_q<S, false, kMaxQ, true>(p, st, max_ctas);
         else if (dbg) small ? launch_prep2_q<S, true, 2, false>(p, st, max_ctas) : launch_prep2_q<S, true, kMaxQ, false>(p, st, max_ctas);
         else small ? launch_prep2_q<S, false, 2, false>(p, st, max_ctas) : launch_prep2_q<S, false, kMaxQ, false>(p, st, max_ctas);
@@ -214,6 +219,8 @@ void launch_prep_t(const PrepParams& p, cudaStream_t st, bool dbg, int max_ctas,
 int launch_prep(raisr_ctx* h, const PrepParams& p, int s, cudaStream_t st, bool dbg, int ctas_per_sm = 0)
 {
     const int max_ctas = ctas_per_sm > 0 ? h->sm_count * ctas_per_sm : 0x7fffffff;
+    if (p.cubic && (h->prep_impl != 2 || p.uext_in))
+        return fail(RAISR_E_UNSUPPORTED, "the bicubic cheap upscaler is built for the gray path of prep2_kernel only");
     switch (s) {
     case 2: launch_prep_t<2>(p, st, dbg, max_ctas, h->prep_impl); break;
     case 3: launch_prep_t<3>(p, st, dbg, max_ctas, h->prep_impl); break;
@@ -389,7 +396,7 @@ void fill_params(raisr_ctx* h, const Geometry& g, const uint8_t* dsrc, int sw, i
     pp.uext = uext; pp.uext_pitch = g.uext_pitch; pp.uext_frame_stride = g.uext_frame;
     pp.hash = hash; pp.hash_pitch = g.hash_pitch; pp.hash_plane_stride = g.hash_plane;
     pp.hash_frame_stride = g.hash_frame;
-    pp.n_angle = h->n_angle; pp.n_strength = h->n_strength; pp.n_coherence = h->n_coherence; pp.as_written = h->as_written;
+    pp.n_angle = h->n_angle; pp.n_strength = h->n_strength; pp.n_coherence = h->n_coherence; pp.as_written = h->as_written; pp.cubic = h->cubic;
     memcpy(pp.sq, h->sq, sizeof(pp.sq)); memcpy(pp.cq, h->cq, sizeof(pp.cq));
     fp = FilterParams{};
     fp.uext = pp.uext; fp.uext_pitch = g.uext_pitch; fp.uext_frame_stride = g.uext_frame;
@@ -727,6 +734,7 @@ int raisr_set_option(raisr_t* h, const char* key, long long value)
     if (!strcmp(key, "prep_impl")) { h->prep_impl = value == 1 ? 1 : 2; return 0; }
     if (!strcmp(key, "color_filter_impl")) { h->color_filter_impl = value == 1 ? 1 : 2; return 0; }
     if (!strcmp(key, "quirks")) { h->as_written = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "cheap_upscaler")) { h->cubic = value ? 1 : 0; return 0; }
     if (!strcmp(key, "taps_fp16")) {
         const int v = value ? 1 : 0;
         if (v != h->taps_fp16) {
@@ -1140,7 +1148,7 @@ int raisr_debug_hash(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_
     pp.uext = (float*)h->uext.p; pp.uext_pitch = g.uext_pitch; pp.uext_frame_stride = g.uext_frame;
     pp.hash = (uint8_t*)h->hash.p; pp.hash_pitch = g.hash_pitch; pp.hash_plane_stride = g.hash_plane;
     pp.hash_frame_stride = g.hash_frame;
-    pp.n_angle = h->n_angle; pp.n_strength = h->n_strength; pp.n_coherence = h->n_coherence; pp.as_written = h->as_written;
+    pp.n_angle = h->n_angle; pp.n_strength = h->n_strength; pp.n_coherence = h->n_coherence; pp.as_written = h->as_written; pp.cubic = h->cubic;
     memcpy(pp.sq, h->sq, sizeof(pp.sq)); memcpy(pp.cq, h->cq, sizeof(pp.cq));
     pp.dbg_hash = (int32_t*)dev[0]; pp.dbg_angle = (float*)dev[1]; pp.dbg_l1 = (float*)dev[2];
     pp.dbg_coh = (float*)dev[3]; pp.dbg_u = (float*)dev[4]; pp.dbg_pitch = dw;
@@ -1195,7 +1203,7 @@ int raisr_upsample_band_u8(raisr_t* h, const uint8_t* src_rows_ptr, int sw, int 
     pp.uext = (float*)h->uext.p; pp.uext_pitch = g.uext_pitch; pp.uext_frame_stride = g.uext_frame;
     pp.hash = (uint8_t*)h->hash.p; pp.hash_pitch = g.hash_pitch; pp.hash_plane_stride = g.hash_plane;
     pp.hash_frame_stride = g.hash_frame;
-    pp.n_angle = h->n_angle; pp.n_strength = h->n_strength; pp.n_coherence = h->n_coherence; pp.as_written = h->as_written;
+    pp.n_angle = h->n_angle; pp.n_strength = h->n_strength; pp.n_coherence = h->n_coherence; pp.as_written = h->as_written; pp.cubic = h->cubic;
     memcpy(pp.sq, h->sq, sizeof(pp.sq)); memcpy(pp.cq, h->cq, sizeof(pp.cq));
     if (int rc = launch_prep(h, pp, scale, st, false)) return rc;
     FilterParams fp{};

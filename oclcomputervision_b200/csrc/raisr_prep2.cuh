@@ -55,10 +55,32 @@ __device__ __forceinline__ p2 sqrt2_guarded(float xl, float xh)
     return pk(sl, sh);
 }
 
+// w_k = dot((1, u, u^2, u^3), cubic_matrix[k]) of raisr.cl:63-68,79-98, evaluated left to right
+__device__ __forceinline__ float4 cubic_sample_weights(float u)
+{
+    const float u2 = __fmul_rn(u, u), u3 = __fmul_rn(u2, u);
+    auto w = [&](float m0, float m1, float m2, float m3) {
+        float acc = __fadd_rn(__fmul_rn(1.0f, m0), __fmul_rn(u, m1));
+        acc = __fadd_rn(acc, __fmul_rn(u2, m2));
+        return __fadd_rn(acc, __fmul_rn(u3, m3));
+    };
+    return make_float4(w(0.0f, -0.5f, 1.0f, -0.5f), w(1.0f, 0.0f, -2.5f, 1.5f), w(0.0f, 0.5f, 2.0f, -1.5f), w(0.0f, 0.0f, -0.5f, 0.5f));
+}
+
 constexpr int P2_RPT = PT_H / 8;   // 7 rows per thread in the vertical pass / eigen stage (thread = 2 columns)
 constexpr int P2_D = PH_H / 2;     // 32: phases 1-2 pair tile rows r and r + 32
 constexpr int P2_NU = PU_H - P2_D; // 34 pair rows of U: (n, n + 32), n = 0..33 (rows 32, 33 appear twice)
 constexpr int P2_UPITCH = 74;      // p2 per pair row: 37 x 16 B, odd -> 8 consecutive rows hit 8 bank groups
+
+constexpr int P2W_H = PW_H + 2, P2W_W = PW_W + 2, P2W_PITCH = P2W_W + 1;   // source window incl. the bicubic ring
+
+// Tables of the bicubic stage-1 variant; they live in the first H plane, which is idle until phase 2.
+struct CubicTabs {
+    float4 colw[PU_W];     // x weights of the 4 taps
+    int4 colx[PU_W];       // window-relative x of the 4 taps
+    float4 roww[PU_H];
+    int4 rowy[PU_H];       // window-relative y * pitch
+};
 
 // As PrepSmem, but the upscaled tile is stored as row pairs (n, n + 32) so that phase 2 can run packed.
 struct Prep2Smem {
@@ -68,7 +90,7 @@ struct Prep2Smem {
         struct {
             float h01[2][PH_H * PH_PITCH];
             float lut[256];
-            float win[PW_H * PW_PITCH];
+            float win[P2W_H * P2W_PITCH];
         };
     };
     float colu[PU_W];
@@ -76,9 +98,12 @@ struct Prep2Smem {
     int2 colx[PU_W];        // window-relative x0, x1
     int2 rowy[PU_H];        // window-relative y0*PW_PITCH, y1*PW_PITCH
 };
-static_assert(sizeof(Prep2Smem) <= 75 * 1024, "three prep2 CTAs per SM");
+static_assert(sizeof(Prep2Smem) <= 75 * 1024 && 256 + P2W_H * P2W_PITCH <= PH_H * PH_PITCH && sizeof(CubicTabs) <= sizeof(float) * PH_H * PH_PITCH,
+              "three prep2 CTAs per SM; phase 0-1 scratch fits the idle H planes");
 
-template <int S, bool DBG, int NQ, bool FROM_U = false>
+// CUBIC: stage 1 is the reference's cubic_sample instead of linear_sample (a template parameter so that the
+// default kernel carries none of its registers).
+template <int S, bool DBG, int NQ, bool FROM_U = false, bool CUBIC = false>
 __global__ void __launch_bounds__(PT_THREADS, 3) prep2_kernel(const PrepParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -104,14 +129,20 @@ __global__ void __launch_bounds__(PT_THREADS, 3) prep2_kernel(const PrepParams p
         __syncthreads();
     } else {
     // ---- phase 0a: texel LUT and coordinate tables (raisr.cl:209: divide, then multiply)
+    CubicTabs& ct = *reinterpret_cast<CubicTabs*>(&sm.h01[0][0]);
     sm.lut[tid] = __fdiv_rn((float)tid, 255.0f);
     if (tid < PU_W) {
         int xe = tx0 - kMargin + tid;
         float fx = __fmul_rn(__fdiv_rn((float)xe, (float)(p.dw - 1)), (float)(p.sw - 1));
         float fl = floorf(fx);
         int xi = (int)fl;
-        sm.colu[tid] = __fsub_rn(fx, fl);
-        sm.colx[tid] = make_int2(min(max(xi, 0), p.sw - 1), min(max(xi + 1, 0), p.sw - 1));
+        if (CUBIC) {
+            ct.colw[tid] = cubic_sample_weights(__fsub_rn(fx, fl));
+            ct.colx[tid] = make_int4(min(max(xi - 1, 0), p.sw - 1), min(max(xi, 0), p.sw - 1), min(max(xi + 1, 0), p.sw - 1), min(max(xi + 2, 0), p.sw - 1));
+        } else {
+            sm.colu[tid] = __fsub_rn(fx, fl);
+            sm.colx[tid] = make_int2(min(max(xi, 0), p.sw - 1), min(max(xi + 1, 0), p.sw - 1));
+        }
     } else if (tid >= 128 && tid < 128 + PU_H) {
         int r = tid - 128;
         int ye = p.y0 + ty0 - kMargin + r;  // global output row
@@ -119,31 +150,41 @@ __global__ void __launch_bounds__(PT_THREADS, 3) prep2_kernel(const PrepParams p
         float fl = floorf(fy);
         int yi = (int)fl;
         float v = __fsub_rn(fy, fl);
-        sm.rowv[r] = make_float2(v, __fsub_rn(1.0f, v));
-        int a = min(max(yi, 0), p.sh_glob - 1) - p.src_row0;
-        int b = min(max(yi + 1, 0), p.sh_glob - 1) - p.src_row0;
-        sm.rowy[r] = make_int2(min(max(a, 0), p.src_rows - 1), min(max(b, 0), p.src_rows - 1));
+        auto srow = [&](int y) { return min(max(min(max(y, 0), p.sh_glob - 1) - p.src_row0, 0), p.src_rows - 1); };
+        if (CUBIC) {
+            ct.roww[r] = cubic_sample_weights(v);
+            ct.rowy[r] = make_int4(srow(yi - 1), srow(yi), srow(yi + 1), srow(yi + 2));
+        } else {
+            sm.rowv[r] = make_float2(v, __fsub_rn(1.0f, v));
+            sm.rowy[r] = make_int2(srow(yi), srow(yi + 1));
+        }
     }
     __syncthreads();
     // ---- phase 0b: make the tables window-relative (x0/y0 are monotone, so first/last bound them)
-    const int wx0 = sm.colx[0].x, wy0 = sm.rowy[0].x;
-    const int ww = sm.colx[PU_W - 1].y - wx0 + 1, wh = sm.rowy[PU_H - 1].y - wy0 + 1;
+    const int wx0 = CUBIC ? ct.colx[0].x : sm.colx[0].x, wy0 = CUBIC ? ct.rowy[0].x : sm.rowy[0].x;
+    const int ww = (CUBIC ? ct.colx[PU_W - 1].w : sm.colx[PU_W - 1].y) - wx0 + 1;
+    const int wh = (CUBIC ? ct.rowy[PU_H - 1].w : sm.rowy[PU_H - 1].y) - wy0 + 1;
     __syncthreads();
     if (tid < PU_W) {
-        int2 c = sm.colx[tid];
-        sm.colx[tid] = make_int2(c.x - wx0, c.y - wx0);
+        if (CUBIC) { int4 c = ct.colx[tid]; ct.colx[tid] = make_int4(c.x - wx0, c.y - wx0, c.z - wx0, c.w - wx0); }
+        else { int2 c = sm.colx[tid]; sm.colx[tid] = make_int2(c.x - wx0, c.y - wx0); }
     } else if (tid >= 128 && tid < 128 + PU_H) {
-        int2 r = sm.rowy[tid - 128];
-        sm.rowy[tid - 128] = make_int2((r.x - wy0) * PW_PITCH, (r.y - wy0) * PW_PITCH);
+        if (CUBIC) {
+            int4 r = ct.rowy[tid - 128];
+            ct.rowy[tid - 128] = make_int4((r.x - wy0) * P2W_PITCH, (r.y - wy0) * P2W_PITCH, (r.z - wy0) * P2W_PITCH, (r.w - wy0) * P2W_PITCH);
+        } else {
+            int2 r = sm.rowy[tid - 128];
+            sm.rowy[tid - 128] = make_int2((r.x - wy0) * P2W_PITCH, (r.y - wy0) * P2W_PITCH);
+        }
     }
     // ---- phase 0c: source window -> float texels (read_imagef UNORM8 decode), one LUT hit per texel
     const uint8_t* src = p.src + (size_t)frame * p.src_frame_stride;
-    {   // 64 threads per window row (ww <= PW_W = 40 of them active), four rows per pass: no index division
+    {   // 64 threads per window row (ww <= P2W_W = 42 of them active), four rows per pass: no index division
         const int c = tid & 63;
         if (c < ww) {
             const uint8_t* sp = src + (size_t)(wy0 + (tid >> 6)) * p.src_pitch + wx0 + c;
-            float* wp = &sm.win[(tid >> 6) * PW_PITCH + c];
-            for (int r = tid >> 6; r < wh; r += 4, sp += 4 * p.src_pitch, wp += 4 * PW_PITCH) *wp = sm.lut[__ldg(sp)];
+            float* wp = &sm.win[(tid >> 6) * P2W_PITCH + c];
+            for (int r = tid >> 6; r < wh; r += 4, sp += 4 * p.src_pitch, wp += 4 * P2W_PITCH) *wp = sm.lut[__ldg(sp)];
         }
     }
     __syncthreads();
@@ -171,6 +212,32 @@ __global__ void __launch_bounds__(PT_THREADS, 3) prep2_kernel(const PrepParams p
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int n = min(4 * q + k, P2_NU - 1);
+                if (CUBIC) {   // raisr.cl:99-105: acc += (pix * xweight[j]) * yweight[i], i outer, j inner; clamp to [0,1]
+                    const float4 xw = ct.colw[c];
+                    const int4 xo = ct.colx[c];
+                    float res[2];
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const int r = n + half * P2_D;
+                        const float4 yw = ct.roww[r];
+                        const int4 yo = ct.rowy[r];
+                        const int yoff[4] = {yo.x, yo.y, yo.z, yo.w};
+                        const float ywv[4] = {yw.x, yw.y, yw.z, yw.w};
+                        float acc = 0.0f;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float* wr = sm.win + yoff[i];
+                            acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(wr[xo.x], xw.x), ywv[i]));
+                            acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(wr[xo.y], xw.y), ywv[i]));
+                            acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(wr[xo.z], xw.z), ywv[i]));
+                            acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(wr[xo.w], xw.w), ywv[i]));
+                        }
+                        res[half] = fminf(fmaxf(acc, 0.0f), 1.0f);
+                    }
+                    vl[k] = res[0]; vh[k] = res[1];
+                    if (4 * q + k < P2_NU) sm.u2[n * P2_UPITCH + c] = pk(res[0], res[1]);
+                    continue;
+                }
                 const int2 ya = sm.rowy[n], yb = sm.rowy[n + P2_D];
                 const float2 wa = sm.rowv[n], wb = sm.rowv[n + P2_D];
                 const p2 p00 = pk(sm.win[ya.x + cx.x], sm.win[yb.x + cx.x]), p01 = pk(sm.win[ya.x + cx.y], sm.win[yb.x + cx.y]);

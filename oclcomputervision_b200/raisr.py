@@ -57,14 +57,15 @@ class ClRaisr:
 
     def __init__(self, grayMode, filters: Optional[np.ndarray] = None, device: int = 0,
                  n_angle: int = 24, n_strength: int = 3, n_coherence: int = 3,
-                 filter_path: Optional[str] = None, quirks: str = "intended", taps: str = "fp32"):
+                 filter_path: Optional[str] = None, quirks: str = "intended", taps: str = "fp32",
+                 upscaler: str = "bilinear"):
         """quirks="as_written" reproduces the three slips of the kernel text (raisr.cl:271,310,316);
         taps="fp16" rounds every tap to half precision like the reference's `(half)pf[...]` (raisr.cl:328).
         Both default to the intended fp32 algorithm; arithmetic is fp32 in every mode."""
         if grayMode not in (0, 1):
             raise ValueError("grayMode must be 1 (gray, raisr.py:97-100) or 0 (BGRA, raisr.py:101-104)")
-        if quirks not in ("intended", "as_written") or taps not in ("fp32", "fp16"):
-            raise ValueError("quirks must be 'intended' or 'as_written', taps 'fp32' or 'fp16'")
+        if quirks not in ("intended", "as_written") or taps not in ("fp32", "fp16") or upscaler not in ("bilinear", "bicubic"):
+            raise ValueError("quirks must be 'intended' or 'as_written', taps 'fp32' or 'fp16', upscaler 'bilinear' or 'bicubic'")
         self.grayMode = grayMode
         self.n_angle, self.n_strength, self.n_coherence = n_angle, n_strength, n_coherence
         self._lib = _cabi.load()
@@ -76,6 +77,8 @@ class ClRaisr:
             self.set_option("quirks", 1)
         if taps == "fp16":
             self.set_option("taps_fp16", 1)
+        if upscaler == "bicubic":   # the reference's unused cubic_sample as stage 1 (raisr.cl:63-106)
+            self.set_option("cheap_upscaler", 1)
         # raisr.py:80-82
         g = self.gaussian2d([9, 9], 2)
         g = np.diag(g.ravel()).astype(np.float32)

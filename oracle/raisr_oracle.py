@@ -70,6 +70,51 @@ def _fma(a, b, c):
     return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(F32)
 
 
+CUBIC_MATRIX = np.array([[0.0, -0.5, 1.0, -0.5], [1.0, 0.0, -2.5, 1.5], [0.0, 0.5, 2.0, -1.5], [0.0, 0.0, -0.5, 0.5]], F32)  # raisr.cl:63-68
+
+
+def _cubic_weights(frac: np.ndarray) -> np.ndarray:
+    """(n, 4) weights of raisr.cl:79-88,90-98: w_k = dot((1, u, u^2, u^3), cubic_matrix[k]), left to right."""
+    u = frac.astype(F32)
+    u2 = (u * u).astype(F32)
+    u3 = (u2 * u).astype(F32)
+    w = []
+    for k in range(4):
+        m = CUBIC_MATRIX[k]
+        acc = (F32(1.0) * m[0] + u * m[1]).astype(F32)
+        acc = (acc + u2 * m[2]).astype(F32)
+        acc = (acc + u3 * m[3]).astype(F32)
+        w.append(acc)
+    return np.stack(w, axis=1)
+
+
+def upscale_ext_cubic(src_u8: np.ndarray, s: int) -> np.ndarray:
+    """Stage 1 with the reference's alternative cheap upscaler `cubic_sample` (raisr.cl:63-106, never called by
+    the shipped kernel): 4x4 taps around floor(coord), weights from cubic_matrix,
+    acc += (pix * xweight[j]) * yweight[i] with i outer / j inner, clamp to [0,1].  Same coordinates and
+    CLAMP_TO_EDGE reads as the bilinear stage."""
+    sh, sw = src_u8.shape
+    dw, dh = sw * s, sh * s
+
+    def axis(n_dst, n_src):
+        pos = np.arange(-MARGIN, n_dst + MARGIN, dtype=np.int64).astype(F32)
+        f = (pos / F32(n_dst - 1)) * F32(n_src - 1)
+        fl = np.floor(f)
+        i0 = fl.astype(np.int64)
+        idx = np.stack([np.clip(i0 - 1 + k, 0, n_src - 1) for k in range(4)], axis=1)
+        return idx, _cubic_weights((f - fl).astype(F32))
+
+    xi, xw = axis(dw, sw)
+    yi, yw = axis(dh, sh)
+    p = src_u8.astype(F32) / F32(255.0)
+    acc = np.zeros((yi.shape[0], xi.shape[0]), F32)
+    for i in range(4):
+        for j in range(4):
+            pix = p[np.ix_(yi[:, i], xi[:, j])]
+            acc = (acc + ((pix * xw[None, :, j]).astype(F32) * yw[:, i, None]).astype(F32)).astype(F32)
+    return np.clip(acc, F32(0), F32(1)).astype(F32)
+
+
 def upscale_ext(src_u8: np.ndarray, s: int) -> np.ndarray:
     """Stage 1 on the extended (dh+10, dw+10) domain (raisr.cl:48-61,171-190,198-217)."""
     sh, sw = src_u8.shape
@@ -185,15 +230,16 @@ def gather_dot(Uext, hash_, filters):
 def raisr_ref(src_u8: np.ndarray, filters: Optional[np.ndarray], s: int = 2, *,
               n_angle=24, n_strength=3, n_coherence=3,
               strength_q=DEFAULT_STRENGTH_Q, coherence_q=DEFAULT_COHERENCE_Q,
-              quirks: str = "intended", taps: str = "fp32") -> Dict[str, np.ndarray]:
+              quirks: str = "intended", taps: str = "fp32", upscaler: str = "bilinear") -> Dict[str, np.ndarray]:
     """numpy restatement.  Returns U, Uext, angle, L1, coherence, hash, out_f32, out_u8.
 
+    upscaler: "bilinear" (what raisr.cl:198-217 calls) | "bicubic" (its unused cubic_sample, raisr.cl:63-106).
     quirks: "intended" | "as_written" (see eigen_hash).  taps: "fp32" | "fp16" -- "fp16" rounds every tap
     to half precision first, as the reference's `(half)pf[i*FILTER_LEN+j]` does (raisr.cl:328); the
     arithmetic stays fp32 either way."""
-    assert taps in ("fp32", "fp16")
+    assert taps in ("fp32", "fp16") and upscaler in ("bilinear", "bicubic")
     src_u8 = np.ascontiguousarray(src_u8, dtype=np.uint8)
-    Uext = upscale_ext(src_u8, s)
+    Uext = upscale_ext(src_u8, s) if upscaler == "bilinear" else upscale_ext_cubic(src_u8, s)
     ma, mb, md = tensor(Uext)
     theta, L1, coh, h = eigen_hash(ma, mb, md, s, n_angle, n_strength, n_coherence,
                                    strength_q, coherence_q, quirks)
@@ -252,7 +298,7 @@ def _load():
                                          vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp,
                                          vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int]
         lib.raisr_oracle_run_ex.restype = ctypes.c_int
-        lib.raisr_oracle_run_ex.argtypes = list(lib.raisr_oracle_run.argtypes) + [ctypes.c_int, ctypes.c_int]
+        lib.raisr_oracle_run_ex.argtypes = list(lib.raisr_oracle_run.argtypes) + [ctypes.c_int, ctypes.c_int, ctypes.c_int]
         lib.raisr_oracle_bilinear_u8.restype = ctypes.c_int
         lib.raisr_oracle_bilinear_u8.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t,
                                                  ctypes.c_int, vp]
@@ -276,9 +322,9 @@ def raisr_ref_c(src_u8: np.ndarray, filters: Optional[np.ndarray], s: int = 2, *
                 strength_q=DEFAULT_STRENGTH_Q, coherence_q=DEFAULT_COHERENCE_Q,
                 nthreads: int = 0, want=("U", "Uext", "angle", "L1", "coherence", "hash",
                                          "out_f32", "out_u8"),
-                quirks: str = "intended", taps: str = "fp32") -> Dict[str, np.ndarray]:
+                quirks: str = "intended", taps: str = "fp32", upscaler: str = "bilinear") -> Dict[str, np.ndarray]:
     """C restatement (oracle/raisr_oracle.c).  Same keys and options as raisr_ref."""
-    assert quirks in ("intended", "as_written") and taps in ("fp32", "fp16")
+    assert quirks in ("intended", "as_written") and taps in ("fp32", "fp16") and upscaler in ("bilinear", "bicubic")
     lib = _load()
     src_u8 = np.ascontiguousarray(src_u8, dtype=np.uint8)
     sh, sw = src_u8.shape
@@ -307,7 +353,7 @@ def raisr_ref_c(src_u8: np.ndarray, filters: Optional[np.ndarray], s: int = 2, *
                                  n_angle, n_strength, n_coherence, sq.ctypes.data, cq.ctypes.data,
                                  ptr("U"), ptr("Uext"), ptr("angle"), ptr("L1"), ptr("coherence"),
                                  ptr("hash"), ptr("out_f32"), ptr("out_u8"), int(nthreads),
-                                 int(quirks == "as_written"), int(taps == "fp16"))
+                                 int(quirks == "as_written"), int(taps == "fp16"), int(upscaler == "bicubic"))
     if rc != 0:
         raise RuntimeError("raisr_oracle_run failed (%d)" % rc)
     return res

@@ -188,3 +188,23 @@ def test_oracle_quirks_and_taps_switches():
     # fp16 taps == running with a table that was rounded beforehand
     q = flt.astype(np.float16).astype(np.float32)
     assert np.array_equal(O.raisr_ref(src, q, 2)["out_f32"], O.raisr_ref(src, flt, 2, taps="fp16")["out_f32"])
+
+
+def test_oracle_bicubic_cheap_upscaler():
+    """cubic_sample (raisr.cl:63-106) as stage 1: the two restatements agree bit for bit; a constant image stays
+    constant (the Catmull-Rom weights sum to 1) and the result is clamped to [0, 1]."""
+    from oclcomputervision_b200.synth import random_filters, synthetic_frame
+    src = synthetic_frame(33, 47, seed=5)
+    flt = random_filters(3, seed=2)
+    a = O.raisr_ref(src, flt, 3, upscaler="bicubic")
+    b = O.raisr_ref_c(src, flt, 3, upscaler="bicubic")
+    assert np.array_equal(a["Uext"], b["Uext"]) and np.array_equal(a["L1"], b["L1"])
+    same = a["hash"] == b["hash"]
+    assert (same | (O.edge_distance(a) < 1e-5)).all() and np.abs(a["out_f32"] - b["out_f32"])[same].max() <= 1e-6
+    assert a["Uext"].min() >= 0.0 and a["Uext"].max() <= 1.0
+    flat = O.raisr_ref_c(np.full((9, 11), 200, np.uint8), None, 2, upscaler="bicubic", want=("U",))["U"]
+    assert np.abs(flat - np.float32(200 / 255)).max() < 1e-6
+    edge = np.zeros((8, 8), np.uint8); edge[:, 4:] = 255
+    u_lin = O.raisr_ref_c(edge, None, 2, want=("U",))["U"]
+    u_cub = O.raisr_ref_c(edge, None, 2, upscaler="bicubic", want=("U",))["U"]
+    assert np.abs(u_lin - u_cub).max() > 0.02        # the cubic kernel sharpens the step

@@ -336,3 +336,31 @@ def test_colour_two_plane_filter_equals_per_plane_launches(shape):
         outs.append((dst, r.upsample_f32(bgra, 2)))
         r.close()
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,s", [((40, 56), 2), ((37, 53), 2), ((24, 33), 3), ((19, 21), 4), ((130, 150), 2)])
+def test_bicubic_cheap_upscaler_against_oracle(shape, s):
+    """Stage 1 = the reference's (unused) cubic_sample, raisr.cl:63-106: U bit-exact, the rest to the usual bar."""
+    src = synth.synthetic_frame(shape[0], shape[1], seed=23)
+    flt = synth.random_filters(s, seed=8)
+    want = O.raisr_ref_c(src, flt, s, upscaler="bicubic")
+    assert not np.array_equal(want["U"], O.raisr_ref_c(src, flt, s)["U"])
+    r = ClRaisr(1, device=0, upscaler="bicubic")
+    setattr(r, "filters_x%d" % s, flt)
+    h, ang, l1, coh, u = r.debug_hash(src, s)
+    assert np.array_equal(u, want["U"]) and np.array_equal(l1, want["L1"]) and np.array_equal(coh, want["coherence"])
+    bad = h != want["hash"]
+    assert not (bad & ~(O.edge_distance(want) < 1e-5)).any()
+    assert np.abs(r.upsample_f32(src, s) - want["out_f32"])[~bad].max() <= 1e-4
+    dst = np.empty((shape[0] * s, shape[1] * s), np.uint8)
+    r.upsample(src, dst, s)
+    assert np.abs(dst.astype(int) - want["out_u8"].astype(int))[~bad].max() <= 1
+    r.set_option("prep_impl", 1)
+    with pytest.raises(_cabi.RaisrError):
+        r.upsample(src, dst, s)
+    r.close()
+    c = ClRaisr(0, filters=synth.random_filters(2), device=0, upscaler="bicubic")
+    with pytest.raises(_cabi.RaisrError):
+        c.upsample(np.zeros((8, 8, 4), np.uint8), np.zeros((16, 16, 4), np.uint8), 2)
+    c.close()
