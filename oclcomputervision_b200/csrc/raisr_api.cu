@@ -524,12 +524,26 @@ int upsample_impl(raisr_ctx* h, const uint8_t* src, int sw, int sh, size_t src_p
         if (int rc = h->ddst[b].ensure(dst_frame * chunk)) return rc;
     }
     cudaStream_t sc = h->own_stream, sh2d = h->h2d_stream, sd2h = h->d2h_stream;
-    const int nchunks = (n_frames + chunk - 1) / chunk;
+    // Chunk schedule: full chunks in the middle, short ones at both ends -- the first H2D and the last D2H are
+    // the only copies that cannot hide behind kernels, so they should be small (1, 2, chunk, ..., chunk, 2, 1).
+    std::vector<int> sizes;
+    {
+        int left = n_frames;
+        std::vector<int> tail;
+        if (!h->overlap && chunk >= 4 && n_frames >= 3 * chunk) {
+            sizes = {1, 2};
+            tail = {2, 1};
+            left -= 6;
+        }
+        while (left > 0) { const int n = std::min(chunk, left); sizes.push_back(n); left -= n; }
+        sizes.insert(sizes.end(), tail.begin(), tail.end());
+    }
+    const int nchunks = (int)sizes.size();
     // 64 event slots per host chunk: 0/1 H2D, 2/3 D2H, 4 kernels done, 8.. kernel events of enqueue_frames
     auto E = [&](int c, int k) { return h->ev(16 + (size_t)c * 64 + k); };
     std::vector<int> krc(nchunks, 0);
-    for (int c = 0; c < nchunks; ++c) {
-        const int b = c & 1, f0 = c * chunk, n = std::min(chunk, n_frames - f0);
+    for (int c = 0, f0 = 0; c < nchunks; f0 += sizes[c], ++c) {
+        const int b = c & 1, n = sizes[c];
         if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(sh2d, E(c - 2, 4), 0));  // kernels of chunk c-2 done with dsrc[b]
         CUDA_TRY(cudaEventRecord(E(c, 0), sh2d));
         CUDA_TRY(cudaMemcpyAsync(h->dsrc[b].p, src + (size_t)f0 * src_frame, src_frame * n, cudaMemcpyHostToDevice, sh2d));

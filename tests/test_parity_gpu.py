@@ -364,3 +364,22 @@ def test_bicubic_cheap_upscaler_against_oracle(shape, s):
     with pytest.raises(_cabi.RaisrError):
         c.upsample(np.zeros((8, 8, 4), np.uint8), np.zeros((16, 16, 4), np.uint8), 2)
     c.close()
+
+
+@pytest.mark.gpu
+def test_host_pipeline_ramped_chunks_match_single_frames():
+    """The HOST pipeline runs short chunks first and last (1, 2, chunk..., 2, 1); with a tiny scratch budget a
+    20-frame batch goes through that schedule and must equal frame-by-frame calls."""
+    s, n = 2, 20
+    frames = np.stack([synth.synthetic_frame(120, 200, seed=60 + k) for k in range(n)])
+    flt = synth.random_filters(s, seed=3)
+    r = ClRaisr(1, filters=flt, device=0)
+    per_frame = (240 + 18 + 3) // 4 * 4 * (400 + 10) * 4
+    r.set_option("chunk_budget_bytes", max(4 * per_frame + 64, 1 << 20))
+    dst = np.empty((n, 240, 400), np.uint8)
+    r.upsample_batch(frames, dst, s)
+    one = np.empty((240, 400), np.uint8)
+    for k in range(n):
+        r.upsample(frames[k], one, s)
+        assert np.array_equal(dst[k], one), k
+    r.close()
