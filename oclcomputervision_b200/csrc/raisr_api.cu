@@ -107,6 +107,7 @@ struct raisr_ctx {
     float last_prep_ms = 0, last_filter_ms = 0;
     int filter_impl = 1;  // 0 = block (v1), 1 = octet
     int prep_impl = 2;    // 2 = packed-fp32 prep2_kernel, 1 = scalar prep_kernel
+    int filter_pipe = 1;        // 1 = mbarrier full/empty tile pipeline with a producer warp (default), 0 = CTA-wide barriers per tile
     int color_filter_impl = 2;  // 2 = two planes per CTA (s = 2, fp32 taps), 1 = one launch per plane
     int cubic = 0;        // "cheap_upscaler" option: 1 = bicubic stage 1 (gray path, prep2 kernel)
     int as_written = 0;   // "quirks" option
@@ -281,6 +282,30 @@ int make_uext_tmap(CUtensorMap* tm, const FilterParams& p, int box_rows, int box
     return 0;
 }
 
+// Tensor map over the planar hash image: (x byte, own row, pixel type, frame), one OTW x OTH box per tile.
+int make_hash_tmap(CUtensorMap* tm, const FilterParams& p, int ntypes, int box_w, int box_h)
+{
+    static PFN_tmapEncodeTiled encode = nullptr;
+    if (!encode) {
+        cudaDriverEntryPointQueryResult q;
+        void* fn = nullptr;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn)
+            return fail(RAISR_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        encode = (PFN_tmapEncodeTiled)fn;
+    }
+    const int nf = std::max(p.n_frames, 1);
+    cuuint64_t dims[4] = {(cuuint64_t)p.hash_pitch, (cuuint64_t)p.oh, (cuuint64_t)ntypes, (cuuint64_t)nf};
+    cuuint64_t strides[3] = {(cuuint64_t)p.hash_pitch, (cuuint64_t)p.hash_plane_stride,
+                             (cuuint64_t)(nf > 1 ? p.hash_frame_stride : p.hash_plane_stride * ntypes)};
+    cuuint32_t box[4] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void*)p.hash, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(RAISR_E_CUDA, "cuTensorMapEncodeTiled (hash) failed (%d)", (int)r);
+    return 0;
+}
+
 template <int S, typename OutT, int NBUF, bool H16 = false>
 int launch_filter_octet(raisr_ctx* h, FilterParams p, cudaStream_t st)
 {
@@ -290,14 +315,26 @@ int launch_filter_octet(raisr_ctx* h, FilterParams p, cudaStream_t st)
     p.tiles_y = (p.oh + C::OTH - 1) / C::OTH;
     size_t smem = octet_smem_bytes<S, NBUF>(p.n_buckets, H16);
     if (smem > 227 * 1024) return fail(RAISR_E_UNSUPPORTED, "filter table slice of %d buckets does not fit shared memory", p.n_buckets);
-    CUtensorMap tm;
+    CUtensorMap tm, hm;
     if (int rc = make_uext_tmap(&tm, p, G::PT, G::NCOLS)) return rc;
-    auto kern = filter_octet_kernel<S, OutT, NBUF, H16>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int ntypes = S * S;
     long long ntiles = (long long)p.tiles_x * p.tiles_y * p.n_frames;
     int workers = (int)std::max<long long>(1, std::min<long long>(h->sm_count / ntypes, ntiles));
-    kern<<<workers * ntypes, C::NT, smem, st>>>(p, tm);
+    constexpr bool PIPE = NBUF == 2;
+    if (PIPE && h->filter_pipe && (p.hash_pitch % 16) == 0 && (p.hash_plane_stride % 16) == 0 && (p.hash_frame_stride % 16) == 0 &&
+        (reinterpret_cast<uintptr_t>(p.hash) % 16) == 0) {
+        if (int rc = make_hash_tmap(&hm, p, ntypes, C::OTW, C::OTH)) return rc;
+        auto kern = filter_octet_kernel<S, OutT, NBUF, H16, PIPE>;
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<workers * ntypes, C::NT, smem, st>>>(p, tm, hm);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
+    hm = tm;
+    auto kern = filter_octet_kernel<S, OutT, NBUF, H16, false>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<workers * ntypes, C::NT, smem, st>>>(p, tm, hm);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -746,6 +783,7 @@ int raisr_set_option(raisr_t* h, const char* key, long long value)
     if (!strcmp(key, "filter_impl")) { h->filter_impl = value ? 1 : 0; return 0; }
     if (!strcmp(key, "overlap")) { h->overlap = value ? 1 : 0; return 0; }
     if (!strcmp(key, "prep_impl")) { h->prep_impl = value == 1 ? 1 : 2; return 0; }
+    if (!strcmp(key, "filter_pipe")) { h->filter_pipe = value ? 1 : 0; return 0; }
     if (!strcmp(key, "color_filter_impl")) { h->color_filter_impl = value == 1 ? 1 : 2; return 0; }
     if (!strcmp(key, "quirks")) { h->as_written = value ? 1 : 0; return 0; }
     if (!strcmp(key, "cheap_upscaler")) { h->cubic = value ? 1 : 0; return 0; }

@@ -106,7 +106,8 @@ struct OctetGeom {
     static constexpr int TILE_FLOATS = NCOLS * PT;
     static constexpr int HASH_BYTES = C::OTH * C::OTW;   // one byte per own pixel of the tile
     static constexpr int TILE_BYTES = TILE_FLOATS * 4;
-    static constexpr int BUF_BYTES = (TILE_BYTES + HASH_BYTES + 127) / 128 * 128;
+    static constexpr int HASH_OFF = (TILE_BYTES + 127) / 128 * 128;      // TMA destinations are 128-byte aligned
+    static constexpr int BUF_BYTES = (HASH_OFF + HASH_BYTES + 127) / 128 * 128;
     static_assert(C::IW % 8 == 0 && C::OTW % C::IW == 0 && C::OTW % 16 == 0, "items are whole batches of 8 pixels");
     static_assert((8 * S) % WF == 0 && WF >= kFlen && TILE_BYTES % 16 == 0 && NCOLS <= 256 && PT <= 256, "window period / alignment");
     static_assert(ITEMS == NOCT && (S * C::OTH) % 4 == 0, "one item per octet and tile; tiles start on row quads");
@@ -117,7 +118,7 @@ inline size_t octet_smem_bytes(int n_buckets, bool h16 = false)
 {
     using G = OctetGeom<S>;
     const size_t rec = h16 ? kOctStrideH * 2 : kOctStride * sizeof(float);
-    return (size_t)n_buckets * rec + NBUF * (size_t)G::BUF_BYTES + 16;   // + two mbarriers
+    return (size_t)n_buckets * rec + NBUF * (size_t)G::BUF_BYTES + 32;   // + four mbarriers (full / empty per buffer)
 }
 
 __device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gptr)
@@ -193,6 +194,30 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
         ::"r"(bar), "r"(parity) : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(unsigned bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Producer side of the pipelined kernel: one thread fills a tile buffer with two TMA boxes -- the U tile
+// (as below) and the tile's hash bytes (OTW x OTH box of the planar hash image; rows past the image are
+// zero-filled) -- both signalled on the buffer's "full" mbarrier.
+template <int S>
+__device__ __forceinline__ void octet_issue_tile_tma(const CUtensorMap* tm, const CUtensorMap* hm, unsigned char* buf, unsigned bar,
+                                                     const TileCursor& tc, int type, int py, int px)
+{
+    using C = OctetCfg<S>;
+    using G = OctetGeom<S>;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(buf);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(bar, G::TILE_BYTES + G::HASH_BYTES);
+    const int r0 = (S * tc.ty * C::OTH + py) & ~3, c0 = S * tc.tx * C::OTW + px;
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(sbase), "l"(tm), "r"(r0), "r"(c0), "r"(tc.frame), "r"(bar) : "memory");
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(sbase + G::HASH_OFF), "l"(hm), "r"(tc.tx * C::OTW), "r"(tc.ty * C::OTH), "r"(type), "r"(tc.frame), "r"(bar) : "memory");
+}
+
 // Asynchronous fill of one tile buffer.  The U tile (rows S*oy0+py .., columns S*ox0+px .. of the
 // extended upscaled frame, PT x NCOLS, column-major in HBM and in shared memory) is one TMA box
 // issued by a single thread and signalled on an mbarrier; the tile's hash bytes (OTH rows of OTW
@@ -217,7 +242,7 @@ __device__ __forceinline__ void octet_issue_tile(const FilterParams& p, const CU
     for (int idx = threadIdx.x; idx < C::OTH * H16; idx += C::NT) {
         const int r = idx / H16, c = idx - r * H16;
         const uint8_t* g = hp + (size_t)min(tc.ty * C::OTH + r, p.oh - 1) * p.hash_pitch + tc.tx * C::OTW + 16 * min(c, maxh);
-        cp_async16(sbase + G::TILE_BYTES + 16u * idx, g);
+        cp_async16(sbase + G::HASH_OFF + 16u * idx, g);
     }
 }
 
@@ -226,9 +251,16 @@ __device__ __forceinline__ void octet_issue_tile(const FilterParams& p, const CU
 // tile starts when the current one is done and the co-resident kernel fills the gap.
 // H16: the resident table holds fp16 taps (256-byte records, half the shared-memory tap stream); they are
 // widened to fp32 in registers and the arithmetic is the same fp32 FMA chain.
-template <int S, typename OutT, int NBUF = 2, bool H16 = false>
-__global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const FilterParams p, const __grid_constant__ CUtensorMap tmap)
+// PIPE (NBUF = 2 only): no CTA-wide barrier per tile.  Both buffers are filled by TMA (U tile + hash bytes) and
+// signalled on a "full" mbarrier each; a warp that has finished a tile bumps a per-buffer counter, and the
+// warp that arrives LAST -- at that point nobody reads the buffer any more -- issues the TMA of the tile after
+// next into it.  Warps wait only for the tile they need, so they drift apart and the shared-memory pipe no
+// longer drains at every tile boundary (filter 11.04 -> 10.4 ms per step).
+template <int S, typename OutT, int NBUF = 2, bool H16 = false, bool PIPE = false>
+__global__ void __launch_bounds__(OctetCfg<S>::NT, 1)
+    filter_octet_kernel(const FilterParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap hmap)
 {
+    static_assert(!PIPE || NBUF == 2, "the pipelined kernel is double-buffered");
     using C = OctetCfg<S>;
     using G = OctetGeom<S>;
     constexpr int REC = H16 ? kOctStrideH * 2 : kOctStride * 4;      // bytes per filter record
@@ -237,6 +269,7 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
     unsigned char* buf0 = smem_raw + (size_t)p.n_buckets * REC;
     unsigned char* buf1 = buf0 + (NBUF - 1) * G::BUF_BYTES;
     const unsigned bar0 = (unsigned)__cvta_generic_to_shared(buf1 + G::BUF_BYTES), bar1 = bar0 + 8;
+    int* done_cnt = reinterpret_cast<int*>(buf1 + G::BUF_BYTES + 16);   // warps done with buffer 0 / 1
     const int tid = threadIdx.x;
     const int ntypes = S * S;
     const int type = blockIdx.x % ntypes, worker = blockIdx.x / ntypes, nworkers = gridDim.x / ntypes;
@@ -246,6 +279,8 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
     if (tid == 0) {
         mbar_init(bar0, 1);
         mbar_init(bar1, 1);
+        done_cnt[0] = 0;
+        done_cnt[1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -257,13 +292,25 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
     TileCursor cur, nxt;
     cur.init(min(worker, max(ntiles - 1, 0)), p.tiles_x, p.tiles_y);
     nxt = cur;
-    if (worker < ntiles) octet_issue_tile<S>(p, &tmap, buf0, bar0, cur, type, py, px);   // in flight while the table is copied
-    cp_async_commit();
+    if (!PIPE) {
+        if (worker < ntiles) octet_issue_tile<S>(p, &tmap, buf0, bar0, cur, type, py, px);   // in flight while the table is copied
+        cp_async_commit();
+    }
+    if (PIPE && tid == 0) {
+        // the first two tiles need no release and fly while the table is copied
+        TileCursor pc = cur;
+        int pit = 0;
+        for (int tile = worker; tile < ntiles && pit < 2; tile += nworkers, ++pit) {
+            octet_issue_tile_tma<S>(&tmap, &hmap, pit ? buf1 : buf0, pit ? bar1 : bar0, pc, type, py, px);
+            pc.advance(nworkers, p.tiles_x, p.tiles_y);
+        }
+    }
     {
         const float4* g = reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(p.table) + (size_t)type * p.n_buckets * REC);
         float4* s = reinterpret_cast<float4*>(tab);
         for (int i = tid; i < p.n_buckets * (REC / 16); i += C::NT) s[i] = __ldg(g + i);
     }
+    if (PIPE) __syncthreads();            // table slice resident; the only CTA-wide barrier of the pipelined kernel
 
     // Lane geometry: offsets (floats) from the patch origin of the current pixel in the column-major tile.
     const int off_full = lane8;           // filter row = lane8, column 0
@@ -288,7 +335,9 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
     for (int tile = worker; tile < ntiles; tile += nworkers, ++it) {
         unsigned char* buf = (NBUF == 2 && (it & 1)) ? buf1 : buf0;
         nxt.advance(nworkers, p.tiles_x, p.tiles_y);
-        if (NBUF == 2) {
+        if (PIPE) {
+            mbar_wait((it & 1) ? bar1 : bar0, (it >> 1) & 1);   // U tile and hash bytes of this tile have landed
+        } else if (NBUF == 2) {
             if (tile + nworkers < ntiles)
                 octet_issue_tile<S>(p, &tmap, (it & 1) ? buf0 : buf1, (it & 1) ? bar0 : bar1, nxt, type, py, px);
             cp_async_commit();
@@ -298,7 +347,7 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
             cp_async_wait<0>();
             mbar_wait(bar0, it & 1);
         }
-        __syncthreads();
+        if (!PIPE) __syncthreads();
 
         const int oy = cur.ty * C::OTH + row;
         const int oxs = cur.tx * C::OTW + seg * C::IW;      // first own column of the item
@@ -307,7 +356,7 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
                                                  (size_t)(S * oy + py) * p.dst_pitch);
             const float* base = reinterpret_cast<const float*>(buf) + S * (seg * C::IW) * G::PT + S * row + (py & 3);   // S*OTH % 4 == 0
             const float* pf = base + off_full;
-            const uint2* hrow = reinterpret_cast<const uint2*>(buf + G::TILE_BYTES + row * C::OTW + seg * C::IW);
+            const uint2* hrow = reinterpret_cast<const uint2*>(buf + G::HASH_OFF + row * C::OTW + seg * C::IW);
             // circular register windows: element j of pixel i lives in slot (S*i + j) % W
             float w11[G::WF], w5[G::WP];
 #pragma unroll
@@ -415,13 +464,29 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1) filter_octet_kernel(const 
             }
         }
         cur = nxt;
+        if (PIPE) {
+            __syncwarp();
+            if ((tid & 31) == 0) {
+                __threadfence_block();                                   // this warp's reads of the buffer are done
+                if (atomicAdd(&done_cnt[it & 1], 1) == C::NT / 32 - 1) {  // last warp out refills the buffer
+                    done_cnt[it & 1] = 0;
+                    __threadfence_block();
+                    if (tile + 2 * nworkers < ntiles) {
+                        TileCursor t2 = cur;                             // cur already points at the next tile
+                        t2.advance(nworkers, p.tiles_x, p.tiles_y);
+                        octet_issue_tile_tma<S>(&tmap, &hmap, buf, (it & 1) ? bar1 : bar0, t2, type, py, px);
+                    }
+                }
+            }
+            continue;
+        }
         __syncthreads();   // tile consumed: its buffer may be refilled by the next prefetch
         if (NBUF == 1) {
             if (tile + nworkers < ntiles) octet_issue_tile<S>(p, &tmap, buf0, bar0, nxt, type, py, px);
             cp_async_commit();
         }
     }
-    cp_async_wait<0>();
+    if (!PIPE) cp_async_wait<0>();
 }
 
 }  // namespace raisr
