@@ -353,13 +353,16 @@ int launch_filter_octet2(raisr_ctx* h, FilterParams p, cudaStream_t st)
     if (smem > 227 * 1024) return 1;    // does not fit: the caller falls back to one launch per plane
     FilterParams tp = p;
     tp.n_frames = 4;                     // the tensor map's third dimension walks the planes
-    CUtensorMap tm;
+    CUtensorMap tm, hm;
     if (int rc = make_uext_tmap(&tm, tp, G::PT, G::NCOLS)) return rc;
+    FilterParams hp = p;
+    hp.n_frames = 1;
+    if (int rc = make_hash_tmap(&hm, hp, 4, C::OTW, C::OTH)) return rc;
     CUDA_TRY(cudaFuncSetAttribute(filter_octet2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntypes = 4;
     const long long ntiles = (long long)p.tiles_x * p.tiles_y;
     const int workers = (int)std::max<long long>(1, std::min<long long>(h->sm_count / (2 * ntypes), ntiles));
-    filter_octet2_kernel<<<dim3(workers * ntypes, 2), C::NT, smem, st>>>(p, tm);
+    filter_octet2_kernel<<<dim3(workers * ntypes, 2), C::NT, smem, st>>>(p, tm, hm);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -29,38 +29,33 @@ struct Octet2Geom {
     static constexpr int TILE_BYTES = NCOLS * PT * 4;                       // one plane (what TMA delivers)
     static constexpr int PLANE_BYTES = (TILE_BYTES + 127) / 128 * 128;      // plane stride in the buffer: TMA destinations are 128-B aligned
     static constexpr int HASH_BYTES = C::OTH * C::OTW;
-    static constexpr int BUF_BYTES = (2 * PLANE_BYTES + HASH_BYTES + 127) / 128 * 128;   // two planes + hash
+    static constexpr int HASH_OFF = 2 * PLANE_BYTES;                        // 128-byte aligned: a TMA destination too
+    static constexpr int BUF_BYTES = (HASH_OFF + HASH_BYTES + 127) / 128 * 128;          // two planes + hash
     static_assert(C::OTH * SEGS == NOCT && (S * C::OTH) % 4 == 0, "one item per octet; tiles start on row quads");
 };
 
-inline size_t octet2_smem_bytes(int n_buckets) { return (size_t)n_buckets * kOctStride * sizeof(float) + 2 * (size_t)Octet2Geom::BUF_BYTES + 16; }
+inline size_t octet2_smem_bytes(int n_buckets) { return (size_t)n_buckets * kOctStride * sizeof(float) + 2 * (size_t)Octet2Geom::BUF_BYTES + 32; }
 
-__device__ __forceinline__ void octet2_issue_tile(const FilterParams& p, const CUtensorMap* tm, unsigned char* buf, unsigned bar,
+// One thread fills a buffer: the two plane tiles and the hash bytes of the tile, three TMA boxes on one mbarrier.
+__device__ __forceinline__ void octet2_issue_tile(const CUtensorMap* tm, const CUtensorMap* hm, unsigned char* buf, unsigned bar,
                                                   const TileCursor& tc, int type, int py, int px, int plane0)
 {
     using C = Octet2Cfg;
     using G = Octet2Geom;
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(buf);
-    if (threadIdx.x == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar, 2 * G::TILE_BYTES);
-        const int r0 = (C::S * tc.ty * C::OTH + py) & ~3, c0 = C::S * tc.tx * C::OTW + px;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(bar, 2 * G::TILE_BYTES + G::HASH_BYTES);
+    const int r0 = (C::S * tc.ty * C::OTH + py) & ~3, c0 = C::S * tc.tx * C::OTW + px;
 #pragma unroll
-        for (int k = 0; k < 2; ++k)
-            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                         ::"r"(sbase + k * G::PLANE_BYTES), "l"(tm), "r"(r0), "r"(c0), "r"(plane0 + k), "r"(bar) : "memory");
-    }
-    const uint8_t* hp = p.hash + (size_t)type * p.hash_plane_stride;
-    constexpr int H16 = C::OTW / 16;
-    const int maxh = ((int)p.hash_pitch - tc.tx * C::OTW) / 16 - 1;
-    for (int idx = threadIdx.x; idx < C::OTH * H16; idx += C::NT) {
-        const int r = idx / H16, c = idx - r * H16;
-        const uint8_t* g = hp + (size_t)min(tc.ty * C::OTH + r, p.oh - 1) * p.hash_pitch + tc.tx * C::OTW + 16 * min(c, maxh);
-        cp_async16(sbase + 2 * G::PLANE_BYTES + 16u * idx, g);
-    }
+    for (int k = 0; k < 2; ++k)
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(sbase + k * G::PLANE_BYTES), "l"(tm), "r"(r0), "r"(c0), "r"(plane0 + k), "r"(bar) : "memory");
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(sbase + G::HASH_OFF), "l"(hm), "r"(tc.tx * C::OTW), "r"(tc.ty * C::OTH), "r"(type), "r"(0), "r"(bar) : "memory");
 }
 
-__global__ void __launch_bounds__(Octet2Cfg::NT, 1) filter_octet2_kernel(const FilterParams p, const __grid_constant__ CUtensorMap tmap)
+__global__ void __launch_bounds__(Octet2Cfg::NT, 1)
+    filter_octet2_kernel(const FilterParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap hmap)
 {
     using C = Octet2Cfg;
     using G = Octet2Geom;
@@ -70,6 +65,7 @@ __global__ void __launch_bounds__(Octet2Cfg::NT, 1) filter_octet2_kernel(const F
     unsigned char* buf0 = smem_raw + (size_t)p.n_buckets * kOctStride * sizeof(float);
     unsigned char* buf1 = buf0 + G::BUF_BYTES;
     const unsigned bar0 = (unsigned)__cvta_generic_to_shared(buf1 + G::BUF_BYTES), bar1 = bar0 + 8;
+    int* done_cnt = reinterpret_cast<int*>(buf1 + G::BUF_BYTES + 16);   // warps done with buffer 0 / 1
     const int tid = threadIdx.x;
     const int ntypes = S * S;
     const int type = blockIdx.x % ntypes, worker = blockIdx.x / ntypes, nworkers = gridDim.x / ntypes;
@@ -80,6 +76,8 @@ __global__ void __launch_bounds__(Octet2Cfg::NT, 1) filter_octet2_kernel(const F
     if (tid == 0) {
         mbar_init(bar0, 1);
         mbar_init(bar1, 1);
+        done_cnt[0] = 0;
+        done_cnt[1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -89,13 +87,20 @@ __global__ void __launch_bounds__(Octet2Cfg::NT, 1) filter_octet2_kernel(const F
     TileCursor cur, nxt;
     cur.init(min(worker, max(ntiles - 1, 0)), p.tiles_x, p.tiles_y);
     nxt = cur;
-    if (worker < ntiles) octet2_issue_tile(p, &tmap, buf0, bar0, cur, type, py, px, plane0);
-    cp_async_commit();
+    if (tid == 0) {   // the first two tiles fly while the table is copied
+        TileCursor pc = cur;
+        int pit = 0;
+        for (int tile = worker; tile < ntiles && pit < 2; tile += nworkers, ++pit) {
+            octet2_issue_tile(&tmap, &hmap, pit ? buf1 : buf0, pit ? bar1 : bar0, pc, type, py, px, plane0);
+            pc.advance(nworkers, p.tiles_x, p.tiles_y);
+        }
+    }
     {
         const float4* g = reinterpret_cast<const float4*>(p.table + (size_t)type * p.n_buckets * kOctStride);
         float4* s = reinterpret_cast<float4*>(tab);
         for (int i = tid; i < p.n_buckets * (kOctStride / 4); i += C::NT) s[i] = __ldg(g + i);
     }
+    __syncthreads();   // table slice resident; no CTA-wide barrier after this one (see filter_octet_kernel<PIPE>)
     const int off_full = lane8;
     int off_part[G::NEWP];
     if (lane8 < 6) {
@@ -117,11 +122,7 @@ __global__ void __launch_bounds__(Octet2Cfg::NT, 1) filter_octet2_kernel(const F
     for (int tile = worker; tile < ntiles; tile += nworkers, ++it) {
         unsigned char* buf = (it & 1) ? buf1 : buf0;
         nxt.advance(nworkers, p.tiles_x, p.tiles_y);
-        if (tile + nworkers < ntiles) octet2_issue_tile(p, &tmap, (it & 1) ? buf0 : buf1, (it & 1) ? bar0 : bar1, nxt, type, py, px, plane0);
-        cp_async_commit();
-        cp_async_wait<1>();
         mbar_wait((it & 1) ? bar1 : bar0, (it >> 1) & 1);
-        __syncthreads();
 
         const int oy = cur.ty * C::OTH + row;
         const int oxs = cur.tx * C::OTW + seg * C::IW;
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(Octet2Cfg::NT, 1) filter_octet2_kernel(const F
             const float* baseB = baseA + G::PLANE_BYTES / 4;
             const float* pfA = baseA + off_full;
             const float* pfB = baseB + off_full;
-            const uint2* hrow = reinterpret_cast<const uint2*>(buf + 2 * G::PLANE_BYTES + row * C::OTW + seg * C::IW);
+            const uint2* hrow = reinterpret_cast<const uint2*>(buf + G::HASH_OFF + row * C::OTW + seg * C::IW);
             float wA[G::WF], vA[G::WP], wB[G::WF], vB[G::WP];
 #pragma unroll
             for (int j = 0; j < G::WF; ++j) { wA[j] = 0.0f; wB[j] = 0.0f; }
@@ -232,9 +233,20 @@ __global__ void __launch_bounds__(Octet2Cfg::NT, 1) filter_octet2_kernel(const F
             }
         }
         cur = nxt;
-        __syncthreads();
+        __syncwarp();
+        if ((tid & 31) == 0) {
+            __threadfence_block();                                   // this warp's reads of the buffer are done
+            if (atomicAdd(&done_cnt[it & 1], 1) == C::NT / 32 - 1) {  // last warp out refills the buffer
+                done_cnt[it & 1] = 0;
+                __threadfence_block();
+                if (tile + 2 * nworkers < ntiles) {
+                    TileCursor t2 = cur;
+                    t2.advance(nworkers, p.tiles_x, p.tiles_y);
+                    octet2_issue_tile(&tmap, &hmap, buf, (it & 1) ? bar1 : bar0, t2, type, py, px, plane0);
+                }
+            }
+        }
     }
-    cp_async_wait<0>();
 }
 
 }  // namespace raisr
