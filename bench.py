@@ -35,8 +35,8 @@ FLOP_PER_PX = 412.0                             # SURVEY.md 8(d), minimal form: 
 FLOP_PER_PX_FILTER = 244.0                      # 121 FMA + store: the dominant kernel's share of the 412
 BYTES_PER_PX = 1.0 / (SCALE * SCALE) + 1.0      # u8 in -> u8 out
 # From the committed ncu capture of this command's kernels (profiles/r1i_ncu_summary.txt):
-NCU_FILTER_WAVEFRONTS_PER_PX = 4.83             # l1tex__data_pipe_lsu_wavefronts_mem_shared.sum / output pixels
-NCU_FILTER_DRAM_BYTES_PER_PX = 5.88             # dram__bytes_read.sum + dram__bytes_write.sum, per output pixel
+NCU_FILTER_WAVEFRONTS_PER_PX = 4.915            # l1tex__data_pipe_lsu_wavefronts_mem_shared.sum / output pixels
+NCU_FILTER_DRAM_BYTES_PER_PX = 5.876            # dram__bytes_read.sum + dram__bytes_write.sum, per output pixel
 
 
 def make_inputs(n_frames, rank):
