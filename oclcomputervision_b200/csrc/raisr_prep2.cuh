@@ -21,21 +21,10 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "packed_f32.cuh"
 #include "raisr_prep.cuh"
 
 namespace raisr {
-
-typedef unsigned long long p2;   // two packed fp32 in a 64-bit register pair (.lo, .hi)
-
-__device__ __forceinline__ p2 pk(float lo, float hi) { p2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void upk(p2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ p2 bc(float x) { return pk(x, x); }
-__device__ __forceinline__ p2 add2(p2 a, p2 b) { p2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ p2 sub2(p2 a, p2 b) { p2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ p2 mul2(p2 a, p2 b) { p2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ p2 fma2(p2 a, p2 b, p2 c) { p2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-// c - a*b, one rounding (the -a*b + c step of the sqrt / divide refinements)
-__device__ __forceinline__ p2 fnma2(p2 a, p2 b, p2 c) { return fma2(mul2(a, bc(-1.0f)), b, c); }
 
 // sqrt_rn_guarded of both lanes (same sequence as the scalar helper, see raisr_prep.cuh)
 __device__ __forceinline__ p2 sqrt2_guarded(float xl, float xh)
