@@ -208,3 +208,66 @@ def test_oracle_bicubic_cheap_upscaler():
     u_lin = O.raisr_ref_c(edge, None, 2, want=("U",))["U"]
     u_cub = O.raisr_ref_c(edge, None, 2, upscaler="bicubic", want=("U",))["U"]
     assert np.abs(u_lin - u_cub).max() > 0.02        # the cubic kernel sharpens the step
+
+
+@pytest.mark.parametrize("quirks", ["intended", "as_written"])
+def test_oracle_vs_literal_float64_restatement_of_the_kernel_loops(quirks):
+    """Independent pin of stages 3-7: the kernel text taken literally -- CONV3x3 as a flipped convolution
+    (raisr.cl:43-46,235-253), the NON-separable 9x9 loop with gaussian[j][i] (raisr.cl:258-276), the eigen / hash
+    formulas (raisr.cl:278-317) and the 121-tap loop (raisr.cl:322-330) -- evaluated in float64 with scipy, against
+    the separable fp32 oracle.  Buckets may only differ where the float64 value sits within 1e-4 of a bin edge."""
+    from scipy.signal import convolve2d, correlate2d
+    s = 2
+    src = synth.synthetic_frame(48, 64, seed=9)
+    flt = synth.random_filters(s, seed=3)
+    res = O.raisr_ref(src, flt, s, quirks=quirks)
+    U = res["Uext"].astype(np.float64)                       # stage 1 is pinned separately (float64 test above)
+    sob_x = np.array([[-1, 0, 1], [-2, 0, 2], [-1, 0, 1]], np.float64)   # raisr.py:38-47
+    sob_y = np.array([[-1, -2, -1], [0, 0, 0], [1, 2, 1]], np.float64)
+    gx = convolve2d(U, sob_x, mode="valid")                  # true convolution = kernel flipped on both axes
+    gy = convolve2d(U, sob_y, mode="valid")
+    m, n = 4.0, 4.0
+    yy, xx = np.ogrid[-m:m + 1, -n:n + 1]
+    G = np.exp(-(xx * xx + yy * yy) / 8.0)
+    G /= G.sum()                                             # raisr.py:48-60 with shape 9, sigma 2
+    Gt = G.T                                                 # the kernel indexes gaussian[j][i]
+    win = lambda a: correlate2d(a, Gt, mode="valid")
+    mb = win(gx * gy)
+    ma = mb if quirks == "as_written" else win(gx * gx)
+    md = win(gy * gy)
+    T, D = ma + md, ma * md - mb * mb
+    rad = np.maximum(T * T / 4 - D, 0)
+    L1 = T / 2 + np.sqrt(rad)
+    L2 = np.maximum(T / 2 - np.sqrt(rad), 0)
+    theta = np.arctan2(mb, L1 - md)
+    theta = np.where(theta < 0, theta + np.pi, theta)
+    s1, s2 = np.sqrt(L1), np.sqrt(L2)
+    coh = np.where(s1 + s2 != 0, (s1 - s2) / np.where(s1 + s2 != 0, s1 + s2, 1), 0)
+    a = np.clip((theta / np.pi * 24).astype(int), 0, 23)
+    sq, cq = O.DEFAULT_STRENGTH_Q, O.DEFAULT_COHERENCE_Q
+    si = np.where(L1 < sq[0], 0, np.where(L1 < sq[1], 1, 2))
+    cval = L1 if quirks == "as_written" else coh
+    ci = np.where(cval < cq[0], 0, np.where(cval < cq[1], 1, 2))
+    if quirks == "as_written":
+        si = np.zeros_like(si)
+    dh, dw = a.shape
+    yy, xx = np.mgrid[0:dh, 0:dw]
+    h64 = ((a * 3 + si) * 3 + ci) * 4 + (yy % 2) * 2 + (xx % 2)
+    assert h64.shape == res["hash"].shape
+    bad = h64 != res["hash"]
+    fa = theta / np.pi * 24
+    near = np.minimum(np.abs(fa - np.rint(fa)), np.min([np.abs(L1 - q) / q for q in (sq if quirks == "intended" else cq)], axis=0))
+    if quirks == "intended":
+        near = np.minimum(near, np.min([np.abs(coh - q) for q in cq], axis=0))
+    # two populations may legitimately differ between fp32 and float64: pixels on a bin edge, and numerically flat
+    # pixels (tensor below 1e-9, i.e. gradients under 0.01 LSB: the angle of rounding noise) / near-isotropic ones
+    shaky = (near < 1e-4) | (L1 < 1e-9) | (coh < 0.02)
+    assert (bad & ~shaky).sum() == 0, int((bad & ~shaky).sum())
+    assert (bad & (L1 >= 1e-9)).mean() < 0.005
+    # stage 7 literally: i outer, j inner over the 11x11 patch with the filter of the oracle's own bucket
+    taps = flt.reshape(-1, 121)[res["hash"]]
+    acc = np.zeros((dh, dw))
+    for i in range(11):
+        for j in range(11):
+            acc += U[i:i + dh, j:j + dw] * taps[:, :, i * 11 + j]
+    assert np.abs(np.clip(acc, 0, 1) - res["out_f32"]).max() < 5e-6
