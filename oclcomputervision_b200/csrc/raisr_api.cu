@@ -1129,15 +1129,12 @@ static int histeq_apply(raisr_t* h, const uint8_t* src, int w, int hgt, size_t s
     LutParams lp{io.dimg, src_pitch, ddst, dst_pitch, w, hgt, (const uint8_t*)dtable, (const float*)dtable, bw, bh, nx, ny, 0, 0, 0};
     constexpr int kLutSmem = 32 * 1024;
     if (mapping256) {
-        static bool attr_done = false;
-        if (!attr_done) { CUDA_TRY(cudaFuncSetAttribute(lut_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutSmem)); attr_done = true; }
+        // 32 KB of dynamic shared memory: below the 48 KB that needs no opt-in
         const long long chunks = (long long)((w + 15) / 16) * hgt;
         const int ctas = (int)std::max(1LL, std::min<long long>((long long)h->sm_count * 6, (chunks + 2047) / 2048));
         lut_apply_kernel<<<ctas, 256, kLutSmem, io.st>>>(lp);
     } else {
-        static bool attr_done = false;
         constexpr int kBlendSmem = kLutSmem + 4096;
-        if (!attr_done) { CUDA_TRY(cudaFuncSetAttribute(lut_blend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlendSmem)); attr_done = true; }
         // cell k = pixels whose upper-left block index is k; the last cell runs to the image edge
         lp.cells_x = std::min(nx, std::max(0, w - 1 - bw / 2) / bw + 1);
         lp.cells_y = std::min(ny, std::max(0, hgt - 1 - bh / 2) / bh + 1);
