@@ -68,7 +68,10 @@ int raisr_set_stream(raisr_t* h, void* cuda_stream);
  * 0 = block kernel), "chunk_budget_bytes" (size of the per-launch upscaled-image scratch, default 208 MiB),
  * "overlap" (1 = experimental two-stream pipeline that co-schedules the prep kernel of the next chunk
  * with the filter kernel of the current one; default 0, slower on B200), "prep_impl"
- * (2 = packed-fp32 prep2_kernel, default; 1 = scalar prep_kernel; bit-identical results).
+ * (2 = packed-fp32 prep2_kernel, default; 1 = scalar prep_kernel; bit-identical results), "filter_pipe"
+ * (1 = barrier-free tile pipeline in the octet filter kernel, default; 0 = CTA-wide barriers per tile; identical
+ * results), "color_filter_impl" (2 = two planes per CTA in the colour path, default; 1 = one launch per plane;
+ * identical results).
  * Semantics switches, both default 0 = the intended fp32 algorithm:
  *   "quirks"    1 = "as written": the three slips of the shipped kernel text are reproduced --
  *               ma accumulates gx*gy (raisr.cl:271), the coherence bucket compares L1 (raisr.cl:310),

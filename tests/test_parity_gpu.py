@@ -383,3 +383,22 @@ def test_host_pipeline_ramped_chunks_match_single_frames():
         r.upsample(frames[k], one, s)
         assert np.array_equal(dst[k], one), k
     r.close()
+
+
+@pytest.mark.gpu
+def test_filter_pipe_option_is_result_neutral():
+    """`filter_pipe` (barrier-free tile pipeline) and `prep_impl` only change scheduling: outputs are bit-identical."""
+    s = 2
+    frames = np.stack([synth.synthetic_frame(300, 420, seed=70 + k) for k in range(3)])
+    flt = synth.random_filters(s, seed=1)
+    outs = []
+    for pipe, prep in ((1, 2), (0, 2), (1, 1), (0, 1)):
+        r = ClRaisr(1, filters=flt, device=0)
+        r.set_option("filter_pipe", pipe)
+        r.set_option("prep_impl", prep)
+        dst = np.empty((3, 600, 840), np.uint8)
+        r.upsample_batch(frames, dst, s)
+        outs.append(dst)
+        r.close()
+    for o in outs[1:]:
+        assert np.array_equal(outs[0], o)
