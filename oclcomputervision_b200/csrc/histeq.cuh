@@ -13,6 +13,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "packed_f32.cuh"
+
 namespace raisr {
 
 constexpr int kHistBins = 256;     // HIST_BINS,       eq_opencl.py:13
@@ -186,6 +188,21 @@ __device__ __forceinline__ float blend_px(const float4 f, float w00, float w01, 
 }
 __device__ __forceinline__ uint32_t blend_byte(float r) { return __float_as_uint(r) & 0xffu; }
 
+// Same value as blend_px(f, oms*omt, s*omt, oms*t, s*t) with the eight products issued as four packed FMUL2
+// (os = (1-s, s) of the pixel's column, tt = (t, 1-t) of its row); the three additions stay scalar -- ptxas would
+// contract a packed multiply feeding a packed add into one FFMA2 and drop a rounding.
+__device__ __forceinline__ float blend_px_packed(const float4 f, p2 os, float t, float omt)
+{
+    float p00, p01, p10, p11;
+    upk(mul2(mul2(os, bc(omt)), pk(f.x, f.y)), p00, p01);
+    upk(mul2(mul2(os, bc(t)), pk(f.z, f.w)), p10, p11);
+    float acc = __fadd_rn(p00, p01);
+    acc = __fadd_rn(acc, p10);
+    acc = __fadd_rn(acc, p11);
+    acc = fminf(fmaxf(acc, 0.0f), 255.0f);
+    return __fadd_rz(acc, 8388608.0f);
+}
+
 __global__ void __launch_bounds__(256) lut_blend_kernel(const LutParams p)
 {
     extern __shared__ float4 lut4[];                         // [256][8] replicated + [256] staging
@@ -256,7 +273,7 @@ __global__ void __launch_bounds__(256) lut_blend_kernel(const LutParams p)
                         for (int i = 0; i < 4; ++i) {
                             const int c = 4 * h + i;
                             const float4 f = mylut[((vin[h] >> (8 * i)) & 0xffu) << 3];
-                            b[i] = __float_as_uint(blend_px(f, __fmul_rn(oms[c], omt), __fmul_rn(s[c], omt), __fmul_rn(oms[c], t), __fmul_rn(s[c], t)));
+                            b[i] = __float_as_uint(blend_px_packed(f, pk(oms[c], s[c]), t, omt));
                         }
                         // low mantissa byte of each result = the truncated value (hist.cl:144)
                         o[h] = __byte_perm(__byte_perm(b[0], b[1], 0x0040), __byte_perm(b[2], b[3], 0x0040), 0x5410);
