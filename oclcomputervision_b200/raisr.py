@@ -137,19 +137,25 @@ class ClRaisr:
     upscale = upsample  # name used by BASELINE.json's north_star
 
     def upsample_batch(self, src, dst, scale_factor):
-        """src (N, sh, sw) u8 -> dst (N, s*sh, s*sw) u8 or float32, host arrays; frames pipelined."""
+        """Host arrays, frames pipelined (H2D / kernels / D2H on three streams).
+        gray:   src (N, sh, sw) u8        -> dst (N, s*sh, s*sw) u8 or float32
+        colour: src (N, sh, sw, 4) u8 BGRA -> dst (N, s*sh, s*sw, 4) u8 or float32"""
         if scale_factor not in self._filters:
             print('Fatal. not trained for scale factor {}'.format(scale_factor))
             return
-        if src.ndim != 3 or dst.ndim != 3 or src.shape[0] != dst.shape[0]:
-            raise ValueError("upsample_batch expects (N, h, w) arrays")
+        nd = 4 if self.grayMode == 0 else 3
+        if src.ndim != nd or dst.ndim != nd or src.shape[0] != dst.shape[0] or (nd == 4 and (src.shape[3] != 4 or dst.shape[3] != 4)):
+            raise ValueError("upsample_batch expects (N, h, w) arrays in gray mode and (N, h, w, 4) BGRA arrays in colour mode")
         if src.dtype != np.uint8 or not src.flags.c_contiguous or not dst.flags.c_contiguous:
             raise ValueError("src must be C-contiguous uint8 and dst C-contiguous")
-        fn = {np.dtype(np.uint8): self._lib.raisr_upsample_u8, np.dtype(np.float32): self._lib.raisr_upsample_f32}.get(dst.dtype)
+        if self.grayMode == 0:
+            fn = {np.dtype(np.uint8): self._lib.raisr_upsample_bgra_u8, np.dtype(np.float32): self._lib.raisr_upsample_bgra_f32}.get(dst.dtype)
+        else:
+            fn = {np.dtype(np.uint8): self._lib.raisr_upsample_u8, np.dtype(np.float32): self._lib.raisr_upsample_f32}.get(dst.dtype)
         if fn is None:
             raise ValueError("dst must be uint8 or float32")
         ms = (ctypes.c_float * 3)()
-        n, sh, sw = src.shape
+        n, sh, sw = src.shape[:3]
         _cabi.check(fn(self._h, src.ctypes.data, sw, sh, src.strides[1], dst.ctypes.data, dst.shape[2], dst.shape[1],
                        dst.strides[1], int(scale_factor), n, _cabi.RAISR_HOST, ms))
         return get_elapsed_ms(ms)

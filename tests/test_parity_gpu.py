@@ -402,3 +402,28 @@ def test_filter_pipe_option_is_result_neutral():
         r.close()
     for o in outs[1:]:
         assert np.array_equal(outs[0], o)
+
+
+@pytest.mark.gpu
+def test_colour_batch_equals_single_frames():
+    """`upsample_batch` in colour mode pipelines BGRA frames through the host path; each frame equals a single call."""
+    rng = np.random.default_rng(5)
+    n, sh, sw = 5, 72, 100
+    batch = rng.integers(0, 256, (n, sh, sw, 4), dtype=np.uint8)
+    for k in range(n):
+        for c in range(3):
+            batch[k, :, :, c] = synth.synthetic_frame(sh, sw, seed=90 + 3 * k + c)
+    r = ClRaisr(0, filters=synth.random_filters(2, seed=7), device=0)
+    dst = np.empty((n, 2 * sh, 2 * sw, 4), np.uint8)
+    ms = r.upsample_batch(batch, dst, 2)
+    assert len(ms) == 3
+    one = np.empty((2 * sh, 2 * sw, 4), np.uint8)
+    for k in range(n):
+        r.upsample(batch[k], one, 2)
+        assert np.array_equal(dst[k], one), k
+    dstf = np.empty((n, 2 * sh, 2 * sw, 4), np.float32)
+    r.upsample_batch(batch, dstf, 2)
+    assert np.abs(dstf * 255 - dst).max() <= 0.5 + 1e-3
+    with pytest.raises(ValueError):
+        r.upsample_batch(batch[..., 0], dst[..., 0], 2)
+    r.close()
