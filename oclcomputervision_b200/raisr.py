@@ -45,15 +45,14 @@ class ClRaisr:
     sobelY = np.array([-1, -2, -1, 0, 0, 0, 1, 2, 1], dtype=np.float32)
 
     def gaussian2d(self, shape=(3, 3), sigma=0.5):
-        """fspecial('gaussian') (raisr.py:48-60)."""
-        m, n = [(ss - 1.) / 2. for ss in shape]
-        y, x = np.ogrid[-m:m + 1, -n:n + 1]
-        h = np.exp(-(x * x + y * y) / (2. * sigma * sigma))
-        h[h < np.finfo(h.dtype).eps * h.max()] = 0
-        sumh = h.sum()
-        if sumh != 0:
-            h /= sumh
-        return h
+        """Normalised 2-D Gaussian mask, MATLAB fspecial('gaussian') convention (same result as raisr.py:48-60)."""
+        half_r, half_c = (float(shape[0]) - 1.0) / 2.0, (float(shape[1]) - 1.0) / 2.0
+        rows = np.arange(-half_r, half_r + 1.0)[:, None]
+        cols = np.arange(-half_c, half_c + 1.0)[None, :]
+        mask = np.exp(-(cols * cols + rows * rows) / (2.0 * sigma * sigma))
+        mask[mask < np.finfo(mask.dtype).eps * mask.max()] = 0     # fspecial's cut-off (a no-op for 9x9, sigma 2)
+        total = mask.sum()
+        return mask / total if total != 0 else mask
 
     def __init__(self, grayMode, filters: Optional[np.ndarray] = None, device: int = 0,
                  n_angle: int = 24, n_strength: int = 3, n_coherence: int = 3,

@@ -40,15 +40,15 @@ DEFAULT_COHERENCE_Q = np.array([0.25, 0.5], dtype=F32)  # raisr.py:114
 
 
 def gaussian2d(shape=(3, 3), sigma=0.5) -> np.ndarray:
-    """fspecial('gaussian') as the reference builds it (raisr.py:48-60)."""
-    m, n = [(ss - 1.0) / 2.0 for ss in shape]
-    y, x = np.ogrid[-m : m + 1, -n : n + 1]
-    h = np.exp(-(x * x + y * y) / (2.0 * sigma * sigma))
-    h[h < np.finfo(h.dtype).eps * h.max()] = 0
-    sumh = h.sum()
-    if sumh != 0:
-        h /= sumh
-    return h
+    """The reference's Gaussian mask (raisr.py:48-60, MATLAB fspecial('gaussian')): exp(-(x^2+y^2)/(2 sigma^2)) on the
+    centred integer grid, entries below eps*max zeroed, normalised to sum 1 (float64)."""
+    half_r, half_c = (float(shape[0]) - 1.0) / 2.0, (float(shape[1]) - 1.0) / 2.0
+    rows = np.arange(-half_r, half_r + 1.0)[:, None]
+    cols = np.arange(-half_c, half_c + 1.0)[None, :]
+    mask = np.exp(-(cols * cols + rows * rows) / (2.0 * sigma * sigma))
+    mask[mask < np.finfo(mask.dtype).eps * mask.max()] = 0
+    total = mask.sum()
+    return mask / total if total != 0 else mask
 
 
 def reference_gaussian81() -> np.ndarray:
