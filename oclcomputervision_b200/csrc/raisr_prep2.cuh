@@ -155,15 +155,16 @@ __global__ void __launch_bounds__(PT_THREADS, 3) prep2_kernel(const PrepParams p
     const int wh = (CUBIC ? ct.rowy[PU_H - 1].w : sm.rowy[PU_H - 1].y) - wy0 + 1;
     __syncthreads();
     if (tid < PU_W) {
-        if (CUBIC) { int4 c = ct.colx[tid]; ct.colx[tid] = make_int4(c.x - wx0, c.y - wx0, c.z - wx0, c.w - wx0); }
-        else { int2 c = sm.colx[tid]; sm.colx[tid] = make_int2(c.x - wx0, c.y - wx0); }
+        // window-relative BYTE offsets: a texel address is then one integer add away (shared base + row + column)
+        if (CUBIC) { int4 c = ct.colx[tid]; ct.colx[tid] = make_int4(4 * (c.x - wx0), 4 * (c.y - wx0), 4 * (c.z - wx0), 4 * (c.w - wx0)); }
+        else { int2 c = sm.colx[tid]; sm.colx[tid] = make_int2(4 * (c.x - wx0), 4 * (c.y - wx0)); }
     } else if (tid >= 128 && tid < 128 + PU_H) {
         if (CUBIC) {
             int4 r = ct.rowy[tid - 128];
-            ct.rowy[tid - 128] = make_int4((r.x - wy0) * P2W_PITCH, (r.y - wy0) * P2W_PITCH, (r.z - wy0) * P2W_PITCH, (r.w - wy0) * P2W_PITCH);
+            ct.rowy[tid - 128] = make_int4((r.x - wy0) * (4 * P2W_PITCH), (r.y - wy0) * (4 * P2W_PITCH), (r.z - wy0) * (4 * P2W_PITCH), (r.w - wy0) * (4 * P2W_PITCH));
         } else {
             int2 r = sm.rowy[tid - 128];
-            sm.rowy[tid - 128] = make_int2((r.x - wy0) * P2W_PITCH, (r.y - wy0) * P2W_PITCH);
+            sm.rowy[tid - 128] = make_int2((r.x - wy0) * (4 * P2W_PITCH), (r.y - wy0) * (4 * P2W_PITCH));
         }
     }
     // ---- phase 0c: source window -> float texels (read_imagef UNORM8 decode), one LUT hit per texel
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(PT_THREADS, 3) prep2_kernel(const PrepParams p
         const int2 cx = sm.colx[c];
         const float u = sm.colu[c], omu = __fsub_rn(1.0f, u);
         const p2 U2 = bc(u), OMU2 = bc(omu);
+        auto W = [&](int byte_off) { return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(sm.win) + byte_off); };
         const int ge = tx0 + c;  // extended-domain column
         const bool col_owned = ge < ext_w && min(max(ge - kMargin, 0), p.dw - 1) / PT_W == bx;
         const int lo = (by == 0) ? 0 : ty0 + 4;
@@ -215,11 +217,10 @@ __global__ void __launch_bounds__(PT_THREADS, 3) prep2_kernel(const PrepParams p
                         float acc = 0.0f;
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const float* wr = sm.win + yoff[i];
-                            acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(wr[xo.x], xw.x), ywv[i]));
-                            acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(wr[xo.y], xw.y), ywv[i]));
-                            acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(wr[xo.z], xw.z), ywv[i]));
-                            acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(wr[xo.w], xw.w), ywv[i]));
+                            acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(W(yoff[i] + xo.x), xw.x), ywv[i]));
+                            acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(W(yoff[i] + xo.y), xw.y), ywv[i]));
+                            acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(W(yoff[i] + xo.z), xw.z), ywv[i]));
+                            acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(W(yoff[i] + xo.w), xw.w), ywv[i]));
                         }
                         res[half] = fminf(fmaxf(acc, 0.0f), 1.0f);
                     }
@@ -229,8 +230,8 @@ __global__ void __launch_bounds__(PT_THREADS, 3) prep2_kernel(const PrepParams p
                 }
                 const int2 ya = sm.rowy[n], yb = sm.rowy[n + P2_D];
                 const float2 wa = sm.rowv[n], wb = sm.rowv[n + P2_D];
-                const p2 p00 = pk(sm.win[ya.x + cx.x], sm.win[yb.x + cx.x]), p01 = pk(sm.win[ya.x + cx.y], sm.win[yb.x + cx.y]);
-                const p2 p10 = pk(sm.win[ya.y + cx.x], sm.win[yb.y + cx.x]), p11 = pk(sm.win[ya.y + cx.y], sm.win[yb.y + cx.y]);
+                const p2 p00 = pk(W(ya.x + cx.x), W(yb.x + cx.x)), p01 = pk(W(ya.x + cx.y), W(yb.x + cx.y));
+                const p2 p10 = pk(W(ya.y + cx.x), W(yb.y + cx.x)), p11 = pk(W(ya.y + cx.y), W(yb.y + cx.y));
                 const p2 V = pk(wa.x, wb.x), OMV = pk(wa.y, wb.y);
                 float al, ah, tl, th;
                 upk(mul2(mul2(OMU2, OMV), p00), al, ah);
