@@ -26,20 +26,26 @@
 
 namespace raisr {
 
-// sqrt_rn_guarded of both lanes (same sequence as the scalar helper, see raisr_prep.cuh)
+// sqrt_rn_guarded of both lanes (same values as the scalar helper in raisr_prep.cuh: negative / NaN -> 0, else the
+// correctly rounded root).  The refinement is run on x itself with rsqrt(max(x, 1e-30)): that is the scalar fast
+// path for x >= 1e-30 and yields exactly 0 for x == 0 (s = 0, residual 0), so the very common zeros of flat
+// regions need no branch; only 0 < x < 1e-30 (one unsigned compare per lane) takes the IEEE square root.
 __device__ __forceinline__ p2 sqrt2_guarded(float xl, float xh)
 {
-    const float cl = fmaxf(xl, 1.0e-30f), ch = fmaxf(xh, 1.0e-30f);
+    xl = fmaxf(xl, 0.0f);
+    xh = fmaxf(xh, 0.0f);
     float rl, rh;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rl) : "f"(cl));
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rh) : "f"(ch));
-    const p2 x = pk(cl, ch), r = pk(rl, rh);
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rl) : "f"(fmaxf(xl, 1.0e-30f)));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rh) : "f"(fmaxf(xh, 1.0e-30f)));
+    const p2 x = pk(xl, xh), r = pk(rl, rh);
     const p2 s = mul2(x, r), h = mul2(r, bc(0.5f));
     float sl, sh;
     upk(fma2(fnma2(s, s, x), h, s), sl, sh);
-    if (!(fminf(xl, xh) >= 1.0e-30f)) {     // rare: practically only exact zeros
-        if (!(xl >= 1.0e-30f)) sl = xl > 0.0f ? __fsqrt_rn(xl) : 0.0f;
-        if (!(xh >= 1.0e-30f)) sh = xh > 0.0f ? __fsqrt_rn(xh) : 0.0f;
+    const unsigned tiny = __float_as_uint(1.0e-30f) - 1u;     // (bits - 1) < tiny  <=>  0 < x < 1e-30
+    const bool slow_l = (__float_as_uint(xl) - 1u) < tiny, slow_h = (__float_as_uint(xh) - 1u) < tiny;
+    if (slow_l | slow_h) {
+        if (slow_l) sl = __fsqrt_rn(xl);
+        if (slow_h) sh = __fsqrt_rn(xh);
     }
     return pk(sl, sh);
 }
@@ -383,7 +389,7 @@ __global__ void __launch_bounds__(PT_THREADS, 3) prep2_kernel(const PrepParams p
             const p2 rad = sub2(mul2(mul2(T, T), bc(0.25f)), D);     // (a fused T*T*0.25 - D is the same value: *0.25 is exact)
             float radl, radh;
             upk(rad, radl, radh);
-            const p2 sqr = sqrt2_guarded(fmaxf(radl, 0.0f), fmaxf(radh, 0.0f));   // radicand clamped at 0
+            const p2 sqr = sqrt2_guarded(radl, radh);   // radicand clamped at 0 inside
             const p2 ht = mul2(T, bc(0.5f));
             const p2 L1 = add2(ht, sqr);
             float L1l, L1h, L2l, L2h, mbl, mbh, xl, xh;
@@ -425,21 +431,26 @@ __global__ void __launch_bounds__(PT_THREADS, 3) prep2_kernel(const PrepParams p
             // coherence = (sqrt(L1) - sqrt(L2)) / (sqrt(L1) + sqrt(L2)), 0 when the denominator is 0
             float col, coh;
             {
-                const p2 s1 = sqrt2_guarded(L1l, L1h), s2 = sqrt2_guarded(fmaxf(L2l, 0.0f), fmaxf(L2h, 0.0f));   // L2 clamped at 0
+                const p2 s1 = sqrt2_guarded(L1l, L1h), s2 = sqrt2_guarded(L2l, L2h);   // L2 clamped at 0 inside
                 const p2 den = add2(s1, s2), num = sub2(s1, s2);
                 float dl, dh, nl, nh;
                 upk(den, dl, dh);
                 upk(num, nl, nh);
+                // den >= 0.  The refinement runs on den itself with rcp(max(den, 1e-30)): the scalar fast path for
+                // den in [1e-15, 1e15] and exactly 0 for den == 0 (num is 0 then), the reference's "coherence = 0";
+                // anything else (never seen in practice) takes the IEEE divide.
                 float rl, rh;
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rl) : "f"(dl));
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rh) : "f"(dh));
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rl) : "f"(fmaxf(dl, 1.0e-30f)));
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rh) : "f"(fmaxf(dh, 1.0e-30f)));
                 p2 r = pk(rl, rh);
                 r = fma2(r, fnma2(den, r, bc(1.0f)), r);
                 const p2 qq = mul2(num, r);
                 upk(fma2(r, fnma2(den, qq, num), qq), col, coh);
-                if (!(fminf(dl, dh) >= 1.0e-15f && fmaxf(dl, dh) <= 1.0e15f)) {
-                    if (!(dl >= 1.0e-15f && dl <= 1.0e15f)) col = dl != 0.0f ? __fdiv_rn(nl, dl) : 0.0f;
-                    if (!(dh >= 1.0e-15f && dh <= 1.0e15f)) coh = dh != 0.0f ? __fdiv_rn(nh, dh) : 0.0f;
+                const unsigned lo = __float_as_uint(1.0e-15f) - 1u;   // (bits - 1) < lo  <=>  0 < den < 1e-15
+                const bool slow_l = ((__float_as_uint(dl) - 1u) < lo) | !(dl <= 1.0e15f), slow_h = ((__float_as_uint(dh) - 1u) < lo) | !(dh <= 1.0e15f);
+                if (slow_l | slow_h) {
+                    if (slow_l) col = __fdiv_rn(nl, dl);
+                    if (slow_h) coh = __fdiv_rn(nh, dh);
                 }
             }
             // theta / pi with the divide's own fast path (theta is 0 or in [1e-8, pi]; exact for theta = 0)
@@ -450,8 +461,12 @@ __global__ void __launch_bounds__(PT_THREADS, 3) prep2_kernel(const PrepParams p
                 const p2 th = pk(thl, thh);
                 const p2 q = mul2(th, bc(r));
                 upk(fma2(bc(r), fma2(bc(-PI_F), q, th), q), tql, tqh);
-                if (thl != 0.0f && thl < 1.0e-15f) tql = __fdiv_rn(thl, PI_F);
-                if (thh != 0.0f && thh < 1.0e-15f) tqh = __fdiv_rn(thh, PI_F);
+                const unsigned lo = __float_as_uint(1.0e-15f) - 1u;   // theta >= 0: (bits - 1) < lo  <=>  0 < theta < 1e-15
+                const bool slow_l = (__float_as_uint(thl) - 1u) < lo, slow_h = (__float_as_uint(thh) - 1u) < lo;
+                if (slow_l | slow_h) {
+                    if (slow_l) tql = __fdiv_rn(thl, PI_F);
+                    if (slow_h) tqh = __fdiv_rn(thh, PI_F);
+                }
             }
             float fal, fah;
             upk(mul2(pk(tql, tqh), bc((float)p.n_angle)), fal, fah);   // == (theta / pi) * n_angle of the oracle
