@@ -1022,7 +1022,7 @@ int raisr_resize_u8(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_p
     }
     cudaEventRecord(h->ev(1), st);
     ResizeParams rp{dsrc, src_pitch, src_frame, ddst, dst_pitch, dst_frame, sw, sh, dw, dh, channels, mode};
-    dim3 grid((dw + 255) / 256, dh, n_frames);
+    dim3 grid((dw + 255) / 256, (dh + kResizeRows - 1) / kResizeRows, n_frames);
     if (channels == 4) resize_kernel<4><<<grid, 256, 0, st>>>(rp);
     else resize_kernel<1><<<grid, 256, 0, st>>>(rp);
     h->launches++;

@@ -8,8 +8,7 @@
 //                            texel position = (x/(wout-1))*win - 0.5 (OpenCL 1.2 spec 8.2, fp32 weights;
 //                            a hardware sampler would use 8-bit fixed-point weights)
 // All reads go through CLAMP_TO_EDGE; the store is write_imagef to UNORM_INT8 (saturate, round to
-// nearest even).  fp32 with explicit _rn intrinsics, bit-identical to oracle/raisr_oracle.c.  These
-// kernels are pure streaming work (HBM-bound, no reuse worth staging): one thread per output pixel.
+// nearest even).  fp32 with explicit _rn intrinsics, bit-identical to oracle/raisr_oracle.c.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -38,63 +37,153 @@ __device__ __forceinline__ void cubic_weights(float u, float w[4])
     w[3] = __fadd_rn(__fmul_rn(u2, -0.5f), __fmul_rn(u3, 0.5f));
 }
 
+// One CTA = 256 output columns x kResizeRows output rows.  Everything that depends only on the column (source
+// x indices, x weights) is computed once per thread, everything that depends only on the row once per CTA (a small
+// shared table).  The source window the tile needs is decoded ONCE into shared memory as floats (exact quotients
+// v/255, the read_imagef UNORM8 decode) -- this is the reference's "_lds" idea (interpolation.cl:17-71) -- so the
+// per-pixel loop is 4 (bilinear) or 16 (bicubic) shared loads per channel and no global gathers.  Strong
+// down-scaling makes the window too large for shared memory; such tiles read global memory through a 256-entry
+// decode table instead.  (The first version recomputed two coordinate divisions and up to 64 decode divisions for
+// every output pixel and ran at 1-5 % of the HBM roofline, tools/bench_resize.py.)
+constexpr int kResizeRows = 16;
+constexpr int kResizeWin = 10240;             // floats of decoded source window per CTA (40 KB)
+
 template <int CH>
 __global__ void __launch_bounds__(256) resize_kernel(const ResizeParams p)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= p.dw) return;
-    const uint8_t* src = p.src + (size_t)blockIdx.z * p.src_frame_stride;
-    uint8_t* dst = p.dst + (size_t)blockIdx.z * p.dst_frame_stride + (size_t)y * p.dst_pitch + (size_t)x * CH;
-    float fx, fy;
-    if (p.mode == 2) {
-        fx = __fsub_rn(__fmul_rn(__fdiv_rn((float)x, (float)(p.dw - 1)), (float)p.sw), 0.5f);
-        fy = __fsub_rn(__fmul_rn(__fdiv_rn((float)y, (float)(p.dh - 1)), (float)p.sh), 0.5f);
-    } else {
-        fx = __fmul_rn(__fdiv_rn((float)x, (float)(p.dw - 1)), (float)(p.sw - 1));
-        fy = __fmul_rn(__fdiv_rn((float)y, (float)(p.dh - 1)), (float)(p.sh - 1));
-    }
-    const float flx = floorf(fx), fly = floorf(fy);
-    const int xi = (int)flx, yi = (int)fly;
-    const float u = __fsub_rn(fx, flx), v = __fsub_rn(fy, fly);
-    float out[CH];
-    if (p.mode != 1) {
-        const int x0 = min(max(xi, 0), p.sw - 1), x1 = min(max(xi + 1, 0), p.sw - 1);
-        const uint8_t* r0 = src + (size_t)min(max(yi, 0), p.sh - 1) * p.src_pitch;
-        const uint8_t* r1 = src + (size_t)min(max(yi + 1, 0), p.sh - 1) * p.src_pitch;
-        const float omu = __fsub_rn(1.0f, u), omv = __fsub_rn(1.0f, v);
-        const float w00 = __fmul_rn(omu, omv), w01 = __fmul_rn(u, omv), w10 = __fmul_rn(omu, v), w11 = __fmul_rn(u, v);
+    __shared__ float win[kResizeWin];
+    __shared__ float lut[256];
+    __shared__ int rowoff[kResizeRows][4];      // clamped source row indices (2 used by the bilinear modes)
+    __shared__ float roww[kResizeRows][4];      // bilinear: (1-v, v); bicubic: the four y weights
+    __shared__ int wbox[2];                     // first / last source column of the tile
+    const int tid = threadIdx.x;
+    const int x = min(blockIdx.x * 256 + tid, p.dw - 1), y0 = blockIdx.y * kResizeRows;
+    const bool active = blockIdx.x * 256 + tid < p.dw;
+    const int rows = min(kResizeRows, p.dh - y0);
+    const int ntap = p.mode == 1 ? 4 : 2, first_tap = p.mode == 1 ? -1 : 0;
+    lut[tid] = __fdiv_rn((float)tid, 255.0f);
+    if (tid < kResizeRows) {
+        const int y = min(y0 + tid, p.dh - 1);
+        const float fy = p.mode == 2 ? __fsub_rn(__fmul_rn(__fdiv_rn((float)y, (float)(p.dh - 1)), (float)p.sh), 0.5f)
+                                     : __fmul_rn(__fdiv_rn((float)y, (float)(p.dh - 1)), (float)(p.sh - 1));
+        const float fly = floorf(fy);
+        const int yi = (int)fly;
+        const float v = __fsub_rn(fy, fly);
+        if (p.mode != 1) {
+            rowoff[tid][0] = min(max(yi, 0), p.sh - 1); rowoff[tid][1] = min(max(yi + 1, 0), p.sh - 1);
+            roww[tid][0] = __fsub_rn(1.0f, v); roww[tid][1] = v;
+        } else {
+            float yw[4];
+            cubic_weights(v, yw);
 #pragma unroll
-        for (int c = 0; c < CH; ++c) {
-            float acc = __fmul_rn(w00, unorm8(__ldg(r0 + x0 * CH + c)));
-            acc = __fadd_rn(acc, __fmul_rn(w01, unorm8(__ldg(r0 + x1 * CH + c))));
-            acc = __fadd_rn(acc, __fmul_rn(w10, unorm8(__ldg(r1 + x0 * CH + c))));
-            acc = __fadd_rn(acc, __fmul_rn(w11, unorm8(__ldg(r1 + x1 * CH + c))));
-            out[c] = acc;
+            for (int i = 0; i < 4; ++i) { rowoff[tid][i] = min(max(yi - 1 + i, 0), p.sh - 1); roww[tid][i] = yw[i]; }
         }
-    } else {
-        float xw[4], yw[4];
-        cubic_weights(u, xw);
-        cubic_weights(v, yw);
+    }
+    const uint8_t* src = p.src + (size_t)blockIdx.z * p.src_frame_stride;
+    uint8_t* dcol = p.dst + (size_t)blockIdx.z * p.dst_frame_stride + (size_t)x * CH;
+    const float fx = p.mode == 2 ? __fsub_rn(__fmul_rn(__fdiv_rn((float)x, (float)(p.dw - 1)), (float)p.sw), 0.5f)
+                                 : __fmul_rn(__fdiv_rn((float)x, (float)(p.dw - 1)), (float)(p.sw - 1));
+    const float flx = floorf(fx);
+    const int xi = (int)flx;
+    const float u = __fsub_rn(fx, flx);
+    int xs[4];
 #pragma unroll
-        for (int c = 0; c < CH; ++c) out[c] = 0.0f;
+    for (int j = 0; j < 4; ++j) xs[j] = min(max(xi + first_tap + j, 0), p.sw - 1);
+    // clamped indices are monotone in x and y: the first / last thread and row bound the window
+    if (tid == 0) wbox[0] = xs[0];
+    if (tid == 255) wbox[1] = xs[ntap - 1];
+    __syncthreads();
+    const int wx0 = wbox[0], ww = wbox[1] - wx0 + 1;
+    const int wy0 = rowoff[0][0], wh = rowoff[rows - 1][ntap - 1] - wy0 + 1;
+    const bool staged = ww * wh * CH <= kResizeWin;          // CTA-uniform
+    const bool src4 = CH == 4 && ((reinterpret_cast<uintptr_t>(src) | p.src_pitch) & 3) == 0;
+    __syncthreads();                                         // everybody has read the absolute row table
+    if (staged) {
+        // window-relative float offsets: a tap address is then row offset + column offset
+        if (tid < kResizeRows) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint8_t* r = src + (size_t)min(max(yi - 1 + i, 0), p.sh - 1) * p.src_pitch;
+            for (int i = 0; i < 4; ++i) rowoff[tid][i] = (rowoff[tid][i] - wy0) * ww * CH;
+        }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int xx = min(max(xi - 1 + j, 0), p.sw - 1);
+        for (int j = 0; j < 4; ++j) xs[j] = (xs[j] - wx0) * CH;
+        for (int idx = tid; idx < ww * wh; idx += 256) {
+            const int r = idx / ww, c = idx - r * ww;
+            const uint8_t* sp = src + (size_t)(wy0 + r) * p.src_pitch + (size_t)(wx0 + c) * CH;
+            if (CH == 4 && src4) {
+                const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(sp));
+                *reinterpret_cast<float4*>(&win[4 * idx]) = make_float4(lut[w & 0xffu], lut[(w >> 8) & 0xffu], lut[(w >> 16) & 0xffu], lut[w >> 24]);
+            } else {
 #pragma unroll
-                for (int c = 0; c < CH; ++c)
-                    out[c] = __fadd_rn(out[c], __fmul_rn(__fmul_rn(unorm8(__ldg(r + xx * CH + c)), xw[j]), yw[i]));
+                for (int ch = 0; ch < CH; ++ch) win[CH * idx + ch] = lut[__ldg(sp + ch)];
             }
         }
+        __syncthreads();
     }
-    if (CH == 4) {
-        *reinterpret_cast<uchar4*>(dst) = make_uchar4(to_unorm8(out[0]), to_unorm8(out[1 % CH]), to_unorm8(out[2 % CH]), to_unorm8(out[3 % CH]));
-    } else {
+    if (!active) return;
+    // one source pixel -> CH decoded channels, from the staged window or (fallback) from global memory
+    auto fetch_win = [&](int ry, int xx, float (&px)[CH]) {
+        const float* w = &win[ry + xx];
+        if (CH == 4) { const float4 f = *reinterpret_cast<const float4*>(w); px[0] = f.x; px[1 % CH] = f.y; px[2 % CH] = f.z; px[3 % CH] = f.w; }
+        else px[0] = w[0];
+    };
+    auto fetch_gmem = [&](int ry, int xx, float (&px)[CH]) {
+        const uint8_t* row = src + (size_t)ry * p.src_pitch;
+        if (CH == 4 && src4) {
+            const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(row) + xx);
+            px[0] = lut[w & 0xffu]; px[1 % CH] = lut[(w >> 8) & 0xffu]; px[2 % CH] = lut[(w >> 16) & 0xffu]; px[3 % CH] = lut[w >> 24];
+        } else {
 #pragma unroll
-        for (int c = 0; c < CH; ++c) dst[c] = to_unorm8(out[c]);
-    }
+            for (int c = 0; c < CH; ++c) px[c] = lut[__ldg(row + xx * CH + c)];
+        }
+    };
+    auto store = [&](uint8_t* d, const float (&out)[CH]) {
+        if (CH == 4) *reinterpret_cast<uchar4*>(d) = make_uchar4(to_unorm8(out[0]), to_unorm8(out[1 % CH]), to_unorm8(out[2 % CH]), to_unorm8(out[3 % CH]));
+        else d[0] = to_unorm8(out[0]);
+    };
+    auto run = [&](auto fetch) {
+        if (p.mode != 1) {
+            const float omu = __fsub_rn(1.0f, u);
+            for (int r = 0; r < rows; ++r) {
+                const int ya = rowoff[r][0], yb = rowoff[r][1];
+                const float omv = roww[r][0], v = roww[r][1];
+                const float w00 = __fmul_rn(omu, omv), w01 = __fmul_rn(u, omv), w10 = __fmul_rn(omu, v), w11 = __fmul_rn(u, v);
+                float p00[CH], p01[CH], p10[CH], p11[CH], out[CH];
+                fetch(ya, xs[0], p00); fetch(ya, xs[1], p01); fetch(yb, xs[0], p10); fetch(yb, xs[1], p11);
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    float acc = __fmul_rn(w00, p00[c]);
+                    acc = __fadd_rn(acc, __fmul_rn(w01, p01[c]));
+                    acc = __fadd_rn(acc, __fmul_rn(w10, p10[c]));
+                    acc = __fadd_rn(acc, __fmul_rn(w11, p11[c]));
+                    out[c] = acc;
+                }
+                store(dcol + (size_t)(y0 + r) * p.dst_pitch, out);
+            }
+        } else {
+            float xw[4];
+            cubic_weights(u, xw);
+            for (int r = 0; r < rows; ++r) {
+                float out[CH];
+#pragma unroll
+                for (int c = 0; c < CH; ++c) out[c] = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int ry = rowoff[r][i];
+                    const float yw = roww[r][i];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float px[CH];
+                        fetch(ry, xs[j], px);
+#pragma unroll
+                        for (int c = 0; c < CH; ++c) out[c] = __fadd_rn(out[c], __fmul_rn(__fmul_rn(px[c], xw[j]), yw));
+                    }
+                }
+                store(dcol + (size_t)(y0 + r) * p.dst_pitch, out);
+            }
+        }
+    };
+    if (staged) run(fetch_win);
+    else run(fetch_gmem);
 }
 
 }  // namespace raisr
