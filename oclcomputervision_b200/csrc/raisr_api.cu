@@ -837,9 +837,10 @@ int raisr_bilinear_u8(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src
         CUDA_TRY(cudaMemcpyAsync(h->dsrc[0].p, src, src_frame * n_frames, cudaMemcpyHostToDevice, st));
     }
     cudaEventRecord(h->ev(1), st);
-    BilinearParams bp{dsrc, src_pitch, src_frame, ddst, dst_pitch, dst_frame, sw, sh, dw, dh};
-    dim3 grid(((dw + 3) / 4 + 255) / 256, dh, n_frames);
-    bilinear_u8_kernel<<<grid, 256, 0, st>>>(bp);
+    // stage 1 alone == the stand-alone bilinear_lds resizer (same map, same expression order; tests pin the two)
+    ResizeParams rp{dsrc, src_pitch, src_frame, ddst, dst_pitch, dst_frame, sw, sh, dw, dh, 1, 0};
+    dim3 grid((dw + 255) / 256, (dh + kResizeRows - 1) / kResizeRows, n_frames);
+    resize_kernel<1><<<grid, 256, 0, st>>>(rp);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     cudaEventRecord(h->ev(2), st);
