@@ -55,6 +55,20 @@ void raisr_destroy(raisr_t* h);
  * copied (and re-laid-out per pixel type) so the caller may free it.  n_floats is checked. */
 int raisr_set_filters(raisr_t* h, int scale, const float* table, size_t n_floats);
 
+/* What the filter kernel of the gray path multiplies by (no reference counterpart; the parity tests feed it to the
+ * oracle).  table_out (may be NULL) receives the effective taps in the layout of raisr_set_filters: the table as
+ * given for tap format 0 (fp32), every tap rounded to fp16 for format 1, and the 24-bit values for format 2 (sign,
+ * exponent and 15 mantissa bits stored, see csrc/raisr_octet.cuh).  tap_format / b24_bound (may be NULL): the format
+ * in use for this scale, and max over filters of sum_k |tap_b24 - tap| -- a bound on |output - fp32-tap output|. */
+int raisr_get_effective_filters(raisr_t* h, int scale, float* table_out, size_t n_floats, int* tap_format,
+                                float* b24_bound);
+
+/* Host-only helper (needs no device): packs one 11x11 filter (row-major taps) into the 384-byte 24-bit record the
+ * filter kernel keeps in shared memory for this scale and returns the 121 tap values the kernel will decode from it.
+ * Record layout: 24 chunks of 16 bytes; lane p (0..7) owns chunks p, p+8, p+16 = a circular stream of 48 bytes;
+ * slot k (0..15) of the lane is the little-endian 32-bit word starting at stream byte 3k (wrapping at 48). */
+int raisr_pack_taps_b24(const float* filter121, int scale, unsigned char record384[384], float effective121[121]);
+
 /* Replaces clStreQ / clCoheQ (raisr.py:112-115; used at raisr.cl:301-314).  n_sq must be
  * n_strength-1 and n_cq n_coherence-1.  Defaults are {1e-4,1e-3} and {0.25,0.5}. */
 int raisr_set_quantizers(raisr_t* h, const float* strength_q, int n_sq, const float* coherence_q,
@@ -78,8 +92,13 @@ int raisr_set_stream(raisr_t* h, void* cuda_stream);
  *               strength is left out of the hash (raisr.cl:316)
  *   "cheap_upscaler" 1 = stage 1 uses the reference's cubic_sample (raisr.cl:63-106, present in the kernel
  *               source but never called) instead of linear_sample; gray path only
- *   "taps_fp16" 1 = every tap is rounded to fp16 before use, as the reference's `(half)pf[...]`
- *               (raisr.cl:328) does; arithmetic stays fp32.  Re-packs the tables already set. */
+ *   "taps"      precision of the taps in the resident shared-memory table; arithmetic is fp32 in every mode.
+ *               0 = fp32.  1 = fp16, as the reference's `(half)pf[...]` (raisr.cl:328) does.  2 = b24: sign, exponent
+ *               and 15 mantissa bits (three quarters of the tap stream that bounds the filter kernel).  3 = auto
+ *               (default): b24 when sum_k |tap_b24 - tap| <= 5e-5 for every filter of the table, i.e. when the
+ *               output provably stays within half the 1e-4 parity tolerance of the fp32-tap result, else fp32.
+ *               Gray path only; the colour path keeps fp32 (or fp16) taps.  Re-packs the tables already set.
+ *   "taps_fp16" older spelling: 1 = "taps" 1, 0 = "taps" 3. */
 int raisr_set_option(raisr_t* h, const char* key, long long value);
 
 /* Replaces ClRaisr.upsample (raisr.py:85-135) for gray frames: H2D copy, the fused RAISR kernels
@@ -152,6 +171,11 @@ int ocv_histeq_local_block_u8(raisr_t* h, const uint8_t* src, int w, int hgt, si
 int raisr_debug_hash(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_pitch, int scale,
                      int32_t* hash, float* angle, float* l1, float* coherence, float* upscaled,
                      int where);
+
+/* The same probe for the colour path (raisr.py:101-104): BGRA source, the quantities are derived from the Y
+ * plane of the upscaled, colour-converted image (raisr.cl:211-214,235-317).  No U output. */
+int raisr_debug_hash_bgra(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_pitch, int scale,
+                          int32_t* hash, float* angle, float* l1, float* coherence, int where);
 
 /* Row-band form for one very large image split across GPUs (no counterpart in the reference,
  * which is single-device; the coordinate map of raisr.cl:209 must use GLOBAL dimensions).

@@ -21,6 +21,8 @@ SIGNATURES = {
     "raisr_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int]),
     "raisr_destroy": (None, [c_void_p]),
     "raisr_set_filters": (c_int, [c_void_p, c_int, c_void_p, c_size_t]),
+    "raisr_get_effective_filters": (c_int, [c_void_p, c_int, c_void_p, c_size_t, POINTER(c_int), POINTER(c_float)]),
+    "raisr_pack_taps_b24": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "raisr_set_quantizers": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int]),
     "raisr_set_stream": (c_int, [c_void_p, c_void_p]),
     "raisr_set_option": (c_int, [c_void_p, c_char_p, c_longlong]),
@@ -42,6 +44,8 @@ SIGNATURES = {
                                           c_int, c_int, c_int, POINTER(c_float)]),
     "raisr_debug_hash": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_int]),
+    "raisr_debug_hash_bgra": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_int]),
     "raisr_upsample_band_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_int, c_void_p,
                                        c_size_t, c_int, c_int, c_int]),
     "raisr_band_src_rows": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),

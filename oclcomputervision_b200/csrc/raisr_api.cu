@@ -5,34 +5,25 @@
 // buffers, CUDA streams/events and two hand-written sm_100a kernels (raisr_prep.cuh,
 // raisr_filter.cuh).  No CPU fallback: every entry point that needs a device fails with
 // RAISR_E_CUDA when none is usable.
-#include "../../include/raisr_b200.h"
-
-#include <cuda.h>
-#include <cuda_runtime.h>
+#include "raisr_internal.h"
 
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
-#include <string>
-#include <vector>
 
-#include "raisr_filter.cuh"
-#include "raisr_octet.cuh"
-#include "raisr_octet2.cuh"
 #include <cuda_fp16.h>
+#include "raisr_octet.cuh"    // host-side record packers
 #include "histeq.cuh"
 #include "raisr_color.cuh"
-#include "raisr_prep.cuh"
-#include "raisr_prep2.cuh"
 #include "raisr_resize.cuh"
 
 using namespace raisr;
 
 static thread_local std::string g_err;
 
-static int fail(int code, const char* fmt, ...)
+int raisr_fail(int code, const char* fmt, ...)
 {
     char buf[512];
     va_list ap;
@@ -42,89 +33,6 @@ static int fail(int code, const char* fmt, ...)
     g_err = buf;
     return code;
 }
-
-#define CUDA_TRY(expr)                                                                         \
-    do {                                                                                       \
-        cudaError_t e__ = (expr);                                                              \
-        if (e__ != cudaSuccess)                                                                \
-            return fail(e__ == cudaErrorMemoryAllocation ? RAISR_E_NOMEM : RAISR_E_CUDA,       \
-                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__,     \
-                        __LINE__);                                                             \
-    } while (0)
-
-namespace {
-
-struct DevBuf {
-    void* p = nullptr;
-    size_t bytes = 0;
-    int ensure(size_t need)
-    {
-        if (need <= bytes) return 0;
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-        cudaError_t e = cudaMalloc(&p, need);
-        if (e != cudaSuccess) return fail(RAISR_E_NOMEM, "cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
-        bytes = need;
-        return 0;
-    }
-    void release()
-    {
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-    }
-};
-
-struct ScaleTable {
-    DevBuf block;   // [type][bucket][132]  (filter_block_kernel)
-    DevBuf octet;   // [type][bucket][128]  (filter_octet_kernel, lane-major chunks)
-    DevBuf octet16; // [type][bucket][128 halfs]  (filter_octet_kernel<H16>, only with taps_fp16)
-    std::vector<float> host;  // the caller's table as given (repacked when the tap precision option changes)
-    bool set = false;
-};
-
-}  // namespace
-
-struct raisr_ctx {
-    int device = 0;
-    int n_angle = 24, n_strength = 3, n_coherence = 3;
-    int n_buckets = 216;
-    int sm_count = 0, clock_khz = 0;
-    char name[128] = {0};
-    float sq[kMaxQ], cq[kMaxQ];
-    cudaStream_t own_stream = nullptr, h2d_stream = nullptr, d2h_stream = nullptr;
-    cudaStream_t user_stream = nullptr;
-    bool use_user_stream = false;
-    ScaleTable tables[5];  // index = scale (2..4)
-    DevBuf uext, hash, dsrc[2], ddst[2], dbg;
-    DevBuf uext2, hash2;          // second scratch set of the overlapped pipeline
-    DevBuf cplanes;               // colour path: four filtered float planes
-    cudaStream_t prep_stream = nullptr, filt_stream = nullptr;
-    int overlap = 0;              // 1: prep of chunk c+1 shares the SMs with the filter of chunk c
-    std::vector<cudaEvent_t> ev_pool;
-    long long launches = 0;
-    float last_prep_ms = 0, last_filter_ms = 0;
-    int filter_impl = 1;  // 0 = block (v1), 1 = octet
-    int prep_impl = 2;    // 2 = packed-fp32 prep2_kernel, 1 = scalar prep_kernel
-    int filter_pipe = 1;        // 1 = mbarrier full/empty tile pipeline with a producer warp (default), 0 = CTA-wide barriers per tile
-    int color_filter_impl = 2;  // 2 = two planes per CTA (s = 2, fp32 taps), 1 = one launch per plane
-    int cubic = 0;        // "cheap_upscaler" option: 1 = bicubic stage 1 (gray path, prep2 kernel)
-    int as_written = 0;   // "quirks" option
-    int taps_fp16 = 0;    // "taps_fp16" option
-    size_t chunk_budget = 208u << 20;   // upscaled-image scratch per kernel launch: 6 frames of 1080p->4K
-
-    cudaStream_t stream() const { return use_user_stream ? user_stream : own_stream; }
-    cudaEvent_t ev(size_t i)
-    {
-        while (ev_pool.size() <= i) {
-            cudaEvent_t e;
-            cudaEventCreate(&e);
-            ev_pool.push_back(e);
-        }
-        return ev_pool[i];
-    }
-};
 
 namespace {
 
@@ -143,6 +51,15 @@ struct Guard {  // select the handle's device for the duration of a call
 };
 
 size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Host <-> device copy of `rows` image rows of `row_bytes` bytes, both sides at the same byte pitch (a batch is
+// n_frames * height rows at one pitch).  Only the image bytes move: a caller may pass a row-strided view of a
+// larger array (pitch > row_bytes), whose bytes between the rows are neither read nor written.
+cudaError_t copy_rows(void* dst, const void* src, size_t pitch, size_t row_bytes, size_t rows, cudaMemcpyKind kind, cudaStream_t st)
+{
+    if (pitch == row_bytes) return cudaMemcpyAsync(dst, src, pitch * rows, kind, st);
+    return cudaMemcpy2DAsync(dst, pitch, src, pitch, row_bytes, rows, kind, st);
+}
 
 struct Geometry {
     int sw, sh, dw, dh, s;
@@ -169,241 +86,24 @@ Geometry make_geometry(int sw, int rows_out, int s)
     return g;
 }
 
-template <int S, bool DBG, int NQ, bool FROM_U>
-void launch_prep_q(PrepParams p, cudaStream_t st, int max_ctas)
-{
-    p.tiles_x = (p.dw + PT_W - 1) / PT_W;
-    p.tiles_y = (p.rows + PT_H - 1) / PT_H;
-    long long total = (long long)p.tiles_x * p.tiles_y * p.n_frames;
-    int grid = (int)std::max<long long>(1, std::min<long long>(total, max_ctas));
-    size_t smem = sizeof(PrepSmem);
-    cudaFuncSetAttribute(prep_kernel<S, DBG, NQ, FROM_U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    prep_kernel<S, DBG, NQ, FROM_U><<<grid, PT_THREADS, smem, st>>>(p);
-}
-
-template <int S, bool DBG, int NQ, bool FROM_U, bool CUBIC = false>
-void launch_prep2_q(PrepParams p, cudaStream_t st, int max_ctas)
-{
-    p.tiles_x = (p.dw + PT_W - 1) / PT_W;
-    p.tiles_y = (p.rows + PT_H - 1) / PT_H;
-    long long total = (long long)p.tiles_x * p.tiles_y * p.n_frames;
-    int grid = (int)std::max<long long>(1, std::min<long long>(total, max_ctas));
-    size_t smem = sizeof(Prep2Smem);
-    cudaFuncSetAttribute(prep2_kernel<S, DBG, NQ, FROM_U, CUBIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    prep2_kernel<S, DBG, NQ, FROM_U, CUBIC><<<grid, PT_THREADS, smem, st>>>(p);
-}
-
-// impl 2: packed-fp32 kernel (raisr_prep2.cuh, default); impl 1: scalar kernel (raisr_prep.cuh)
-template <int S>
-void launch_prep_t(const PrepParams& p, cudaStream_t st, bool dbg, int max_ctas, int impl)
-{
-    const bool small = p.n_strength <= 3 && p.n_coherence <= 3;   // the reference's 3 x 3 (raisr.cl:9-15)
-    if (impl == 2) {
-        if (p.cubic) {   // optional stage-1 variant: the general-quantiser instantiation only
-            dbg ? launch_prep2_q<S, true, kMaxQ, false, true>(p, st, max_ctas) : launch_prep2_q<S, false, kMaxQ, false, true>(p, st, max_ctas);
-            return;
-        }
-        if (p.uext_in) small ? launch_prep2_q<S, false, 2, true>(p, st, max_ctas) : launch_prep2_q<S, false, kMaxQ, true>(p, st, max_ctas);
-        else if (dbg) small ? launch_prep2_q<S, true, 2, false>(p, st, max_ctas) : launch_prep2_q<S, true, kMaxQ, false>(p, st, max_ctas);
-        else small ? launch_prep2_q<S, false, 2, false>(p, st, max_ctas) : launch_prep2_q<S, false, kMaxQ, false>(p, st, max_ctas);
-        return;
-    }
-    if (p.uext_in) {   // colour path: hash an existing upscaled plane
-        small ? launch_prep_q<S, false, 2, true>(p, st, max_ctas) : launch_prep_q<S, false, kMaxQ, true>(p, st, max_ctas);
-        return;
-    }
-    if (dbg) small ? launch_prep_q<S, true, 2, false>(p, st, max_ctas) : launch_prep_q<S, true, kMaxQ, false>(p, st, max_ctas);
-    else small ? launch_prep_q<S, false, 2, false>(p, st, max_ctas) : launch_prep_q<S, false, kMaxQ, false>(p, st, max_ctas);
-}
-
-// ctas_per_sm == 0: one CTA per tile (the hardware scheduler balances); > 0: persistent grid of that many CTAs per SM
 int launch_prep(raisr_ctx* h, const PrepParams& p, int s, cudaStream_t st, bool dbg, int ctas_per_sm = 0)
 {
-    const int max_ctas = ctas_per_sm > 0 ? h->sm_count * ctas_per_sm : 0x7fffffff;
-    if (p.cubic && (h->prep_impl != 2 || p.uext_in))
-        return fail(RAISR_E_UNSUPPORTED, "the bicubic cheap upscaler is built for the gray path of prep2_kernel only");
-    switch (s) {
-    case 2: launch_prep_t<2>(p, st, dbg, max_ctas, h->prep_impl); break;
-    case 3: launch_prep_t<3>(p, st, dbg, max_ctas, h->prep_impl); break;
-    case 4: launch_prep_t<4>(p, st, dbg, max_ctas, h->prep_impl); break;
-    default: return fail(RAISR_E_UNSUPPORTED, "scale %d not supported (2, 3 or 4)", s);
-    }
-    h->launches++;
-    CUDA_TRY(cudaGetLastError());
-    return 0;
-}
-
-template <int S, typename OutT>
-int launch_filter_block(raisr_ctx* h, FilterParams p, cudaStream_t st)
-{
-    constexpr int OTW = S == 4 ? 32 : 64, OTH = S == 4 ? 16 : 32, BR = 2, BC = 4;
-    using C = BlockCfg<S, OTW, OTH, BR, BC>;
-    p.tiles_x = (p.ow + OTW - 1) / OTW;
-    p.tiles_y = (p.oh + OTH - 1) / OTH;
-    size_t smem = ((size_t)p.n_buckets * kFStride + (size_t)C::TUH * C::TUW) * sizeof(float);
-    if (smem > 227 * 1024) return fail(RAISR_E_UNSUPPORTED, "filter table slice of %d buckets does not fit shared memory", p.n_buckets);
-    auto kern = filter_block_kernel<S, OTW, OTH, BR, BC, OutT>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int ntypes = S * S;
-    long long ntiles = (long long)p.tiles_x * p.tiles_y * p.n_frames;
-    int workers = (int)std::max<long long>(1, std::min<long long>(h->sm_count / ntypes, ntiles));
-    kern<<<workers * ntypes, C::NT, smem, st>>>(p);
-    h->launches++;
-    CUDA_TRY(cudaGetLastError());
-    return 0;
-}
-
-typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-// TMA descriptor of the column-major uext scratch: dims {rows (pitch), columns, frames}, one box =
-// one filter tile (PT rows x NCOLS columns).  The driver entry point is fetched through the runtime,
-// so the library does not link libcuda.
-int make_uext_tmap(CUtensorMap* tm, const FilterParams& p, int box_rows, int box_cols)
-{
-    static PFN_tmapEncodeTiled encode = nullptr;
-    if (!encode) {
-        cudaDriverEntryPointQueryResult q;
-        void* fn = nullptr;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
-        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn)
-            return fail(RAISR_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-        encode = (PFN_tmapEncodeTiled)fn;
-    }
-    cuuint64_t dims[3] = {(cuuint64_t)p.uext_pitch, (cuuint64_t)p.uext_cols, (cuuint64_t)std::max(p.n_frames, 1)};
-    cuuint64_t strides[2] = {(cuuint64_t)p.uext_pitch * sizeof(float), (cuuint64_t)p.uext_frame_stride * sizeof(float)};
-    if (p.n_frames <= 1) strides[1] = (cuuint64_t)p.uext_pitch * p.uext_cols * sizeof(float);
-    cuuint32_t box[3] = {(cuuint32_t)box_rows, (cuuint32_t)box_cols, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)p.uext, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(RAISR_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-    return 0;
-}
-
-// Tensor map over the planar hash image: (x byte, own row, pixel type, frame), one OTW x OTH box per tile.
-int make_hash_tmap(CUtensorMap* tm, const FilterParams& p, int ntypes, int box_w, int box_h)
-{
-    static PFN_tmapEncodeTiled encode = nullptr;
-    if (!encode) {
-        cudaDriverEntryPointQueryResult q;
-        void* fn = nullptr;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
-        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn)
-            return fail(RAISR_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-        encode = (PFN_tmapEncodeTiled)fn;
-    }
-    const int nf = std::max(p.n_frames, 1);
-    cuuint64_t dims[4] = {(cuuint64_t)p.hash_pitch, (cuuint64_t)p.oh, (cuuint64_t)ntypes, (cuuint64_t)nf};
-    cuuint64_t strides[3] = {(cuuint64_t)p.hash_pitch, (cuuint64_t)p.hash_plane_stride,
-                             (cuuint64_t)(nf > 1 ? p.hash_frame_stride : p.hash_plane_stride * ntypes)};
-    cuuint32_t box[4] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void*)p.hash, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(RAISR_E_CUDA, "cuTensorMapEncodeTiled (hash) failed (%d)", (int)r);
-    return 0;
-}
-
-template <int S, typename OutT, int NBUF, bool H16 = false>
-int launch_filter_octet(raisr_ctx* h, FilterParams p, cudaStream_t st)
-{
-    using C = OctetCfg<S>;
-    using G = OctetGeom<S>;
-    p.tiles_x = (p.ow + C::OTW - 1) / C::OTW;
-    p.tiles_y = (p.oh + C::OTH - 1) / C::OTH;
-    size_t smem = octet_smem_bytes<S, NBUF>(p.n_buckets, H16);
-    if (smem > 227 * 1024) return fail(RAISR_E_UNSUPPORTED, "filter table slice of %d buckets does not fit shared memory", p.n_buckets);
-    CUtensorMap tm, hm;
-    if (int rc = make_uext_tmap(&tm, p, G::PT, G::NCOLS)) return rc;
-    int ntypes = S * S;
-    long long ntiles = (long long)p.tiles_x * p.tiles_y * p.n_frames;
-    int workers = (int)std::max<long long>(1, std::min<long long>(h->sm_count / ntypes, ntiles));
-    constexpr bool PIPE = NBUF == 2;
-    if (PIPE && h->filter_pipe && (p.hash_pitch % 16) == 0 && (p.hash_plane_stride % 16) == 0 && (p.hash_frame_stride % 16) == 0 &&
-        (reinterpret_cast<uintptr_t>(p.hash) % 16) == 0) {
-        if (int rc = make_hash_tmap(&hm, p, ntypes, C::OTW, C::OTH)) return rc;
-        auto kern = filter_octet_kernel<S, OutT, NBUF, H16, PIPE>;
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<workers * ntypes, C::NT, smem, st>>>(p, tm, hm);
-        h->launches++;
-        CUDA_TRY(cudaGetLastError());
-        return 0;
-    }
-    hm = tm;
-    auto kern = filter_octet_kernel<S, OutT, NBUF, H16, false>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<workers * ntypes, C::NT, smem, st>>>(p, tm, hm);
-    h->launches++;
-    CUDA_TRY(cudaGetLastError());
-    return 0;
-}
-
-// Colour path, s = 2, fp32 taps: all four planes in one launch, two planes per CTA (raisr_octet2.cuh).
-// `p.uext` / `p.dst` point at plane 0, the frame strides are the plane strides.
-int launch_filter_octet2(raisr_ctx* h, FilterParams p, cudaStream_t st)
-{
-    using C = Octet2Cfg;
-    using G = Octet2Geom;
-    p.tiles_x = (p.ow + C::OTW - 1) / C::OTW;
-    p.tiles_y = (p.oh + C::OTH - 1) / C::OTH;
-    p.table = (const float*)h->tables[2].octet.p;
-    const size_t smem = octet2_smem_bytes(p.n_buckets);
-    if (smem > 227 * 1024) return 1;    // does not fit: the caller falls back to one launch per plane
-    FilterParams tp = p;
-    tp.n_frames = 4;                     // the tensor map's third dimension walks the planes
-    CUtensorMap tm, hm;
-    if (int rc = make_uext_tmap(&tm, tp, G::PT, G::NCOLS)) return rc;
-    FilterParams hp = p;
-    hp.n_frames = 1;
-    if (int rc = make_hash_tmap(&hm, hp, 4, C::OTW, C::OTH)) return rc;
-    CUDA_TRY(cudaFuncSetAttribute(filter_octet2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int ntypes = 4;
-    const long long ntiles = (long long)p.tiles_x * p.tiles_y;
-    const int workers = (int)std::max<long long>(1, std::min<long long>(h->sm_count / (2 * ntypes), ntiles));
-    filter_octet2_kernel<<<dim3(workers * ntypes, 2), C::NT, smem, st>>>(p, tm, hm);
-    h->launches++;
-    CUDA_TRY(cudaGetLastError());
-    return 0;
+    return raisr_launch_prep(h, p, s, st, dbg, ctas_per_sm);
 }
 
 template <typename OutT>
-int launch_filter(raisr_ctx* h, FilterParams p, int s, cudaStream_t st, bool single_buffer = false)
+int launch_filter(raisr_ctx* h, FilterParams p, int s, cudaStream_t st, bool single_buffer = false, bool allow_b24 = true);
+template <>
+int launch_filter<uint8_t>(raisr_ctx* h, FilterParams p, int s, cudaStream_t st, bool single_buffer, bool allow_b24)
 {
-    ScaleTable& t = h->tables[s];
-    if (h->filter_impl == 1) {
-        p.table = (const float*)t.octet.p;
-        if (single_buffer) {
-            switch (s) {
-            case 2: return launch_filter_octet<2, OutT, 1>(h, p, st);
-            case 3: return launch_filter_octet<3, OutT, 1>(h, p, st);
-            case 4: return launch_filter_octet<4, OutT, 1>(h, p, st);
-            }
-        }
-        if (h->taps_fp16 && t.octet16.p) {   // fp16 records in shared memory: half the tap stream
-            p.table = (const float*)t.octet16.p;
-            switch (s) {
-            case 2: return launch_filter_octet<2, OutT, 2, true>(h, p, st);
-            case 3: return launch_filter_octet<3, OutT, 2, true>(h, p, st);
-            case 4: return launch_filter_octet<4, OutT, 2, true>(h, p, st);
-            }
-        }
-        switch (s) {
-        case 2: return launch_filter_octet<2, OutT, 2>(h, p, st);
-        case 3: return launch_filter_octet<3, OutT, 2>(h, p, st);
-        case 4: return launch_filter_octet<4, OutT, 2>(h, p, st);
-        }
-    } else {
-        p.table = (const float*)t.block.p;
-        switch (s) {
-        case 2: return launch_filter_block<2, OutT>(h, p, st);
-        case 3: return launch_filter_block<3, OutT>(h, p, st);
-        case 4: return launch_filter_block<4, OutT>(h, p, st);
-        }
-    }
-    return fail(RAISR_E_UNSUPPORTED, "scale %d not supported", s);
+    return raisr_launch_filter_u8(h, p, s, st, single_buffer, allow_b24);
 }
+template <>
+int launch_filter<float>(raisr_ctx* h, FilterParams p, int s, cudaStream_t st, bool single_buffer, bool allow_b24)
+{
+    return raisr_launch_filter_f32(h, p, s, st, single_buffer, allow_b24);
+}
+int launch_filter_octet2(raisr_ctx* h, FilterParams p, cudaStream_t st) { return raisr_launch_filter_octet2(h, p, st); }
 
 int check_common(raisr_ctx* h, const void* src, int sw, int sh, size_t src_pitch, const void* dst, int dw,
                  int dh, size_t dst_pitch, size_t dst_elem, int scale, int n_frames, bool need_table)
@@ -464,6 +164,7 @@ int enqueue_frames(raisr_ctx* h, const uint8_t* dsrc, int sw, int sh, size_t src
     const int nchunks = (nf + chunk - 1) / chunk;
     PrepParams pp;
     FilterParams fp;
+    h->scratch_acquire(st);
     if (h->overlap && h->filter_impl == 1 && nchunks > 1) {
         // Overlapped pipeline: the prep kernel (instruction-issue bound) of chunk c+1 runs as one
         // persistent CTA per SM next to the single-buffered filter kernel (shared-memory-pipe bound)
@@ -492,6 +193,7 @@ int enqueue_frames(raisr_ctx* h, const uint8_t* dsrc, int sw, int sh, size_t src
         cudaStreamWaitEvent(st, E(nchunks - 1, 3), 0);
         cudaStreamWaitEvent(st, E(nchunks - 1, 1), 0);
         cudaEventRecord(h->ev(ev_base + 1), st);
+        h->scratch_release(st);
         return -1000 - nchunks;   // overlapped: caller reads the event layout above
     }
     for (int f0 = 0; f0 < nf; f0 += chunk) {
@@ -504,6 +206,7 @@ int enqueue_frames(raisr_ctx* h, const uint8_t* dsrc, int sw, int sh, size_t src
         if (int rc = launch_filter<OutT>(h, fp, scale, st)) return rc;
         if (timed) cudaEventRecord(h->ev(e + 2), st);
     }
+    h->scratch_release(st);
     return nchunks;  // number of chunks (>0)
 }
 
@@ -586,7 +289,7 @@ int upsample_impl(raisr_ctx* h, const uint8_t* src, int sw, int sh, size_t src_p
         const int b = c & 1, n = sizes[c];
         if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(sh2d, E(c - 2, 4), 0));  // kernels of chunk c-2 done with dsrc[b]
         CUDA_TRY(cudaEventRecord(E(c, 0), sh2d));
-        CUDA_TRY(cudaMemcpyAsync(h->dsrc[b].p, src + (size_t)f0 * src_frame, src_frame * n, cudaMemcpyHostToDevice, sh2d));
+        CUDA_TRY(copy_rows(h->dsrc[b].p, src + (size_t)f0 * src_frame, src_pitch, (size_t)sw, (size_t)sh * n, cudaMemcpyHostToDevice, sh2d));
         CUDA_TRY(cudaEventRecord(E(c, 1), sh2d));
         CUDA_TRY(cudaStreamWaitEvent(sc, E(c, 1), 0));
         if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(sc, E(c - 2, 3), 0));    // D2H of chunk c-2 done with ddst[b]
@@ -597,7 +300,7 @@ int upsample_impl(raisr_ctx* h, const uint8_t* src, int sw, int sh, size_t src_p
         CUDA_TRY(cudaEventRecord(E(c, 4), sc));
         CUDA_TRY(cudaStreamWaitEvent(sd2h, E(c, 4), 0));
         CUDA_TRY(cudaEventRecord(E(c, 2), sd2h));
-        CUDA_TRY(cudaMemcpyAsync((unsigned char*)dst + (size_t)f0 * dst_frame, h->ddst[b].p, dst_frame * n, cudaMemcpyDeviceToHost, sd2h));
+        CUDA_TRY(copy_rows((unsigned char*)dst + (size_t)f0 * dst_frame, h->ddst[b].p, dst_pitch, (size_t)dw * sizeof(OutT), (size_t)dh * n, cudaMemcpyDeviceToHost, sd2h));
         CUDA_TRY(cudaEventRecord(E(c, 3), sd2h));
     }
     CUDA_TRY(cudaStreamSynchronize(sd2h));
@@ -697,12 +400,13 @@ void raisr_destroy(raisr_t* h)
     if (!h) return;
     Guard guard(h->device);
     cudaDeviceSynchronize();
-    for (auto& t : h->tables) { t.block.release(); t.octet.release(); t.octet16.release(); }
+    for (auto& t : h->tables) { t.block.release(); t.octet.release(); t.octet16.release(); t.b24.release(); }
     h->uext.release(); h->hash.release(); h->dbg.release(); h->uext2.release(); h->hash2.release(); h->cplanes.release();
     if (h->prep_stream) cudaStreamDestroy(h->prep_stream);
     if (h->filt_stream) cudaStreamDestroy(h->filt_stream);
     for (int b = 0; b < 2; ++b) { h->dsrc[b].release(); h->ddst[b].release(); }
     for (auto e : h->ev_pool) cudaEventDestroy(e);
+    if (h->scratch_ev) cudaEventDestroy(h->scratch_ev);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
@@ -735,7 +439,35 @@ static int upload_table(raisr_ctx* h, int scale)
         }
     if (int rc = t.block.ensure(blk.size() * sizeof(float))) return rc;
     if (int rc = t.octet.ensure(oct.size() * sizeof(float))) return rc;
+    // 24-bit records and the bound on what they can change: |out_b24 - out_fp32| <= sum_k |tap_b24 - tap_fp32| * |patch_k|
+    // and the patch is an upscaled image in [0,1] (bilinear; the bicubic variant clamps).  "auto" uses them only while
+    // that bound stays under half of the 1e-4 parity tolerance.
+    std::vector<uint8_t> rec24;
+    std::vector<float> eff24;
+    t.format = h->taps_mode == 1 ? kTapsF16 : kTapsF32;
+    t.b24_bound = 0;
+    if (h->taps_mode >= 2) {
+        rec24.assign((size_t)ss * nb * kOctBytesB24, 0);
+        eff24.assign(t.host.size(), 0.0f);
+        double worst = 0;
+        for (int type = 0; type < ss; ++type)
+            for (int b = 0; b < nb; ++b) {
+                const size_t o = ((size_t)b * ss + type) * kTaps;
+                octet_pack_filter_b24(t.host.data() + o, &rec24[((size_t)type * nb + b) * kOctBytesB24], scale, &eff24[o]);
+                double sum = 0;
+                for (int k = 0; k < kTaps; ++k) sum += fabs((double)eff24[o + k] - (double)t.host[o + k]);
+                worst = std::max(worst, sum);
+            }
+        t.b24_bound = (float)worst;
+        if (h->taps_mode == 2 || worst <= 5.0e-5) t.format = kTapsB24;
+    }
+    if (t.format == kTapsB24) t.eff = eff24;
+    else t.eff.assign(table, table + t.host.size());
+    if (t.format == kTapsB24)
+        if (int rc = t.b24.ensure(rec24.size())) return rc;
     CUDA_TRY(cudaStreamSynchronize(h->stream()));   // a previous launch may still read the old table
+    if (h->scratch_busy) CUDA_TRY(cudaEventSynchronize(h->scratch_ev));
+    if (t.format == kTapsB24) CUDA_TRY(cudaMemcpy(t.b24.p, rec24.data(), rec24.size(), cudaMemcpyHostToDevice));
     if (h->taps_fp16) {
         std::vector<uint16_t> o16((size_t)ss * nb * kOctStrideH, 0);
         auto to_half = [](float v) { return __half_as_ushort(__float2half_rn(v)); };
@@ -760,6 +492,28 @@ int raisr_set_filters(raisr_t* h, int scale, const float* table, size_t n_floats
     if (n_floats != want) return fail(RAISR_E_ARG, "filter table has %zu floats, expected %zu = %d*%d*%d*%d*121", n_floats, want, h->n_angle, h->n_strength, h->n_coherence, ss);
     h->tables[scale].host.assign(table, table + n_floats);
     return upload_table(h, scale);
+}
+
+int raisr_get_effective_filters(raisr_t* h, int scale, float* table_out, size_t n_floats, int* tap_format, float* b24_bound)
+{
+    if (!h) return fail(RAISR_E_ARG, "null handle");
+    if (scale < 2 || scale > 4 || !h->tables[scale].set) return fail(RAISR_E_STATE, "no filter table set for scale %d", scale);
+    const ScaleTable& t = h->tables[scale];
+    if (table_out) {
+        if (n_floats != t.eff.size()) return fail(RAISR_E_ARG, "table_out has %zu floats, the table %zu", n_floats, t.eff.size());
+        memcpy(table_out, t.eff.data(), t.eff.size() * sizeof(float));
+    }
+    if (tap_format) *tap_format = t.format;
+    if (b24_bound) *b24_bound = t.b24_bound;
+    return 0;
+}
+
+int raisr_pack_taps_b24(const float* filter121, int scale, unsigned char record384[384], float effective121[121])
+{
+    if (!filter121 || !record384) return fail(RAISR_E_ARG, "null argument");
+    if (scale < 2 || scale > 4) return fail(RAISR_E_UNSUPPORTED, "scale %d not supported (2, 3 or 4)", scale);
+    octet_pack_filter_b24(filter121, record384, scale, effective121);
+    return 0;
 }
 
 int raisr_set_quantizers(raisr_t* h, const float* strength_q, int n_sq, const float* coherence_q, int n_cq)
@@ -790,10 +544,13 @@ int raisr_set_option(raisr_t* h, const char* key, long long value)
     if (!strcmp(key, "color_filter_impl")) { h->color_filter_impl = value == 1 ? 1 : 2; return 0; }
     if (!strcmp(key, "quirks")) { h->as_written = value ? 1 : 0; return 0; }
     if (!strcmp(key, "cheap_upscaler")) { h->cubic = value ? 1 : 0; return 0; }
-    if (!strcmp(key, "taps_fp16")) {
-        const int v = value ? 1 : 0;
-        if (v != h->taps_fp16) {
-            h->taps_fp16 = v;
+    if (!strcmp(key, "taps_fp16") || !strcmp(key, "taps")) {
+        // "taps": 0 fp32, 1 fp16, 2 b24, 3 auto;  "taps_fp16" (older key): 1 = fp16, 0 = back to the default (auto)
+        int mode = !strcmp(key, "taps") ? (int)value : (value ? 1 : 3);
+        if (mode < 0 || mode > 3) return fail(RAISR_E_ARG, "taps must be 0 (fp32), 1 (fp16), 2 (b24) or 3 (auto)");
+        if (mode != h->taps_mode) {
+            h->taps_mode = mode;
+            h->taps_fp16 = mode == 1;
             for (int sc = 2; sc <= 4; ++sc)
                 if (h->tables[sc].set)
                     if (int rc = upload_table(h, sc)) return rc;
@@ -834,7 +591,7 @@ int raisr_bilinear_u8(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src
         if (int rc = h->ddst[0].ensure(dst_frame * n_frames)) return rc;
         dsrc = (const uint8_t*)h->dsrc[0].p; ddst = (uint8_t*)h->ddst[0].p;
         cudaEventRecord(h->ev(0), st);
-        CUDA_TRY(cudaMemcpyAsync(h->dsrc[0].p, src, src_frame * n_frames, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(copy_rows(h->dsrc[0].p, src, src_pitch, (size_t)sw, (size_t)sh * n_frames, cudaMemcpyHostToDevice, st));
     }
     cudaEventRecord(h->ev(1), st);
     // stage 1 alone == the stand-alone bilinear_lds resizer (same map, same expression order; tests pin the two)
@@ -845,7 +602,7 @@ int raisr_bilinear_u8(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src
     CUDA_TRY(cudaGetLastError());
     cudaEventRecord(h->ev(2), st);
     if (where == RAISR_HOST) {
-        CUDA_TRY(cudaMemcpyAsync(dst, ddst, dst_frame * n_frames, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(copy_rows(dst, ddst, dst_pitch, (size_t)dw, (size_t)dh * n_frames, cudaMemcpyDeviceToHost, st));
         cudaEventRecord(h->ev(3), st);
     }
     if (where == RAISR_HOST || ms) {
@@ -894,7 +651,7 @@ static int enqueue_bgra_frame(raisr_ctx* h, const Geometry& g, const uint8_t* ds
     for (int k = 0; k < 4 && !done; ++k) {
         fp.uext = (const float*)h->uext.p + g.uext_frame * k;
         fp.dst = (float*)h->cplanes.p + fplane * k;
-        if (int rc = launch_filter<float>(h, fp, scale, st)) return rc;
+        if (int rc = launch_filter<float>(h, fp, scale, st, false, false)) return rc;
     }
     ColorPackParams cp{};
     for (int k = 0; k < 4; ++k) cp.plane[k] = (const float*)h->cplanes.p + fplane * k;
@@ -920,6 +677,10 @@ static int upsample_bgra_impl(raisr_t* h, const uint8_t* src, int sw, int sh, si
     if (scale < 2 || scale > 4 || !h->tables[scale].set) return fail(RAISR_E_UNSUPPORTED, "not trained for scale factor %d", scale);
     if (dw != sw * scale || dh != sh * scale) return fail(RAISR_E_ARG, "dst shape %dx%d is not %d x src shape %dx%d", dw, dh, scale, sw, sh);
     if ((src_pitch & 3) || (dst_pitch & 3)) return fail(RAISR_E_ARG, "BGRA pitches must be multiples of 4 bytes");
+    // the kernels read the source as uchar4 and write float4 / uchar4 pixels
+    if (f32 && (dst_pitch & 15)) return fail(RAISR_E_ARG, "float BGRA dst pitch must be a multiple of 16 bytes");
+    if (where == RAISR_DEVICE && (((uintptr_t)src & 3) || ((uintptr_t)dst & (f32 ? 15 : 3))))
+        return fail(RAISR_E_ARG, "device BGRA pointers must be pixel-aligned (src 4 bytes, dst %d bytes)", f32 ? 16 : 4);
     if (h->filter_impl != 1) return fail(RAISR_E_UNSUPPORTED, "the colour path needs the octet filter kernel");
     if (where != RAISR_HOST && where != RAISR_DEVICE) return fail(RAISR_E_ARG, "where must be RAISR_HOST or RAISR_DEVICE");
     Guard guard(h->device);
@@ -931,11 +692,13 @@ static int upsample_bgra_impl(raisr_t* h, const uint8_t* src, int sw, int sh, si
     if (int rc = h->cplanes.ensure(fplane * sizeof(float) * 4)) return rc;
     if (where == RAISR_DEVICE) {
         cudaStream_t st = h->stream();
+        h->scratch_acquire(st);
         cudaEventRecord(h->ev(1), st);
         for (int f = 0; f < n_frames; ++f)
             if (int rc = enqueue_bgra_frame(h, g, src + (size_t)f * src_frame, sw, sh, src_pitch, (unsigned char*)dst + (size_t)f * dst_frame, dst_pitch,
                                             dw, dh, scale, f32, st)) return rc;
         cudaEventRecord(h->ev(2), st);
+        h->scratch_release(st);
         if (ms) {
             CUDA_TRY(cudaStreamSynchronize(st));
             ms[0] = ms[2] = 0;
@@ -950,13 +713,14 @@ static int upsample_bgra_impl(raisr_t* h, const uint8_t* src, int sw, int sh, si
         if (int rc = h->ddst[b].ensure(dst_frame)) return rc;
     }
     cudaStream_t sc = h->own_stream, sh2d = h->h2d_stream, sd2h = h->d2h_stream;
+    h->scratch_acquire(sc);
     // event slots per frame: 0/1 H2D, 2/3 D2H, 5/4 kernels
     auto E = [&](int f, int k) { return h->ev(16 + (size_t)f * 8 + k); };
     for (int f = 0; f < n_frames; ++f) {
         const int b = f & 1;
         if (f >= 2) CUDA_TRY(cudaStreamWaitEvent(sh2d, E(f - 2, 4), 0));   // kernels of frame f-2 are done with dsrc[b]
         CUDA_TRY(cudaEventRecord(E(f, 0), sh2d));
-        CUDA_TRY(cudaMemcpyAsync(h->dsrc[b].p, src + (size_t)f * src_frame, src_frame, cudaMemcpyHostToDevice, sh2d));
+        CUDA_TRY(copy_rows(h->dsrc[b].p, src + (size_t)f * src_frame, src_pitch, (size_t)sw * 4, (size_t)sh, cudaMemcpyHostToDevice, sh2d));
         CUDA_TRY(cudaEventRecord(E(f, 1), sh2d));
         CUDA_TRY(cudaStreamWaitEvent(sc, E(f, 1), 0));
         if (f >= 2) CUDA_TRY(cudaStreamWaitEvent(sc, E(f - 2, 3), 0));     // D2H of frame f-2 is done with ddst[b]
@@ -966,9 +730,10 @@ static int upsample_bgra_impl(raisr_t* h, const uint8_t* src, int sw, int sh, si
         CUDA_TRY(cudaEventRecord(E(f, 4), sc));
         CUDA_TRY(cudaStreamWaitEvent(sd2h, E(f, 4), 0));
         CUDA_TRY(cudaEventRecord(E(f, 2), sd2h));
-        CUDA_TRY(cudaMemcpyAsync((unsigned char*)dst + (size_t)f * dst_frame, h->ddst[b].p, dst_frame, cudaMemcpyDeviceToHost, sd2h));
+        CUDA_TRY(copy_rows((unsigned char*)dst + (size_t)f * dst_frame, h->ddst[b].p, dst_pitch, (size_t)dw * 4 * (f32 ? 4 : 1), (size_t)dh, cudaMemcpyDeviceToHost, sd2h));
         CUDA_TRY(cudaEventRecord(E(f, 3), sd2h));
     }
+    h->scratch_release(sc);
     CUDA_TRY(cudaStreamSynchronize(sd2h));
     CUDA_TRY(cudaStreamSynchronize(sc));
     CUDA_TRY(cudaStreamSynchronize(sh2d));
@@ -1014,12 +779,12 @@ int raisr_resize_u8(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_p
     const uint8_t* dsrc = src;
     uint8_t* ddst = dst;
     if (where == RAISR_HOST) {
-        if (dst_pitch & 3) return fail(RAISR_E_ARG, "dst pitch must be a multiple of 4 bytes");
+        if (channels == 4 && (dst_pitch & 3)) return fail(RAISR_E_ARG, "4-channel dst pitch must be a multiple of 4 bytes");
         if (int rc = h->dsrc[0].ensure(src_frame * n_frames)) return rc;
         if (int rc = h->ddst[0].ensure(dst_frame * n_frames)) return rc;
         dsrc = (const uint8_t*)h->dsrc[0].p; ddst = (uint8_t*)h->ddst[0].p;
         cudaEventRecord(h->ev(0), st);
-        CUDA_TRY(cudaMemcpyAsync(h->dsrc[0].p, src, src_frame * n_frames, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(copy_rows(h->dsrc[0].p, src, src_pitch, (size_t)sw * channels, (size_t)sh * n_frames, cudaMemcpyHostToDevice, st));
     }
     cudaEventRecord(h->ev(1), st);
     ResizeParams rp{dsrc, src_pitch, src_frame, ddst, dst_pitch, dst_frame, sw, sh, dw, dh, channels, mode};
@@ -1030,7 +795,7 @@ int raisr_resize_u8(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_p
     CUDA_TRY(cudaGetLastError());
     cudaEventRecord(h->ev(2), st);
     if (where == RAISR_HOST) {
-        CUDA_TRY(cudaMemcpyAsync(dst, ddst, dst_frame * n_frames, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(copy_rows(dst, ddst, dst_pitch, (size_t)dw * channels, (size_t)dh * n_frames, cudaMemcpyDeviceToHost, st));
         cudaEventRecord(h->ev(3), st);
     }
     if (where == RAISR_HOST || ms) {
@@ -1054,13 +819,13 @@ namespace {
 struct HistIo {
     raisr_ctx* h; cudaStream_t st; int where;
     const uint8_t* dimg = nullptr;
-    int begin(const uint8_t* img, size_t bytes)
+    int begin(const uint8_t* img, size_t pitch, int w, int rows)
     {
         dimg = img;
         cudaEventRecord(h->ev(0), st);
         if (where == RAISR_HOST) {
-            if (int rc = h->dsrc[0].ensure(bytes)) return rc;
-            CUDA_TRY(cudaMemcpyAsync(h->dsrc[0].p, img, bytes, cudaMemcpyHostToDevice, st));
+            if (int rc = h->dsrc[0].ensure(pitch * rows)) return rc;
+            CUDA_TRY(copy_rows(h->dsrc[0].p, img, pitch, (size_t)w, (size_t)rows, cudaMemcpyHostToDevice, st));
             dimg = (const uint8_t*)h->dsrc[0].p;
         }
         return 0;
@@ -1090,7 +855,7 @@ int ocv_hist_grid_u8(raisr_t* h, const uint8_t* img, int w, int hgt, size_t pitc
     HistIo io{h, h->stream(), where};
     const int tx = w / kHistBins, ty = hgt / kHistTileH;
     const size_t out_bytes = (size_t)tx * ty * kHistBins * sizeof(uint32_t);
-    if (int rc = io.begin(img, pitch * hgt)) return rc;
+    if (int rc = io.begin(img, pitch, w, hgt)) return rc;
     uint32_t* dout = hist_out;
     if (where == RAISR_HOST) {
         if (int rc = h->dbg.ensure(out_bytes)) return rc;
@@ -1115,7 +880,7 @@ static int histeq_apply(raisr_t* h, const uint8_t* src, int w, int hgt, size_t s
     if (where != RAISR_HOST && where != RAISR_DEVICE) return fail(RAISR_E_ARG, "where must be RAISR_HOST or RAISR_DEVICE");
     Guard guard(h->device);
     HistIo io{h, h->stream(), where};
-    if (int rc = io.begin(src, src_pitch * hgt)) return rc;
+    if (int rc = io.begin(src, src_pitch, w, hgt)) return rc;
     uint8_t* ddst = dst;
     const size_t table_bytes = mapping256 ? 256 : (size_t)nx * ny * kHistBins * sizeof(float);
     const void* dtable = mapping256 ? (const void*)mapping256 : (const void*)mappings;
@@ -1152,7 +917,7 @@ static int histeq_apply(raisr_t* h, const uint8_t* src, int w, int hgt, size_t s
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     cudaEventRecord(h->ev(2), io.st);
-    if (where == RAISR_HOST) CUDA_TRY(cudaMemcpyAsync(dst, ddst, dst_pitch * hgt, cudaMemcpyDeviceToHost, io.st));
+    if (where == RAISR_HOST) CUDA_TRY(copy_rows(dst, ddst, dst_pitch, (size_t)w, (size_t)hgt, cudaMemcpyDeviceToHost, io.st));
     cudaEventRecord(h->ev(3), io.st);
     return io.finish(ms);
 }
@@ -1190,7 +955,7 @@ int raisr_debug_hash(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_
     if (where == RAISR_HOST) {
         if (int rc = h->dsrc[0].ensure(src_pitch * sh)) return rc;
         if (int rc = h->dbg.ensure(plane * 4 * 5)) return rc;
-        CUDA_TRY(cudaMemcpyAsync(h->dsrc[0].p, src, src_pitch * sh, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(copy_rows(h->dsrc[0].p, src, src_pitch, (size_t)sw, (size_t)sh, cudaMemcpyHostToDevice, st));
         dsrc = (const uint8_t*)h->dsrc[0].p;
         for (int i = 0; i < 5; ++i) dev[i] = outs[i] ? (char*)h->dbg.p + plane * 4 * i : nullptr;
     }
@@ -1205,9 +970,62 @@ int raisr_debug_hash(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_
     memcpy(pp.sq, h->sq, sizeof(pp.sq)); memcpy(pp.cq, h->cq, sizeof(pp.cq));
     pp.dbg_hash = (int32_t*)dev[0]; pp.dbg_angle = (float*)dev[1]; pp.dbg_l1 = (float*)dev[2];
     pp.dbg_coh = (float*)dev[3]; pp.dbg_u = (float*)dev[4]; pp.dbg_pitch = dw;
+    h->scratch_acquire(st);
     if (int rc = launch_prep(h, pp, scale, st, true)) return rc;
+    h->scratch_release(st);
     if (where == RAISR_HOST) {
         for (int i = 0; i < 5; ++i)
+            if (outs[i]) CUDA_TRY(cudaMemcpyAsync(outs[i], dev[i], plane * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int raisr_debug_hash_bgra(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_pitch, int scale, int32_t* hash,
+                          float* angle, float* l1, float* coherence, int where)
+{
+    if (!h || !src) return fail(RAISR_E_ARG, "null argument");
+    if (scale < 2 || scale > 4) return fail(RAISR_E_UNSUPPORTED, "not trained for scale factor %d", scale);
+    if (sw < 1 || sh < 1 || src_pitch < (size_t)sw * 4 || (src_pitch & 3)) return fail(RAISR_E_ARG, "bad source shape / pitch");
+    if (h->prep_impl != 2) return fail(RAISR_E_UNSUPPORTED, "the colour parity probe is built for prep2_kernel only");
+    if (where != RAISR_HOST && where != RAISR_DEVICE) return fail(RAISR_E_ARG, "where must be RAISR_HOST or RAISR_DEVICE");
+    if (where == RAISR_DEVICE && ((uintptr_t)src & 3)) return fail(RAISR_E_ARG, "device BGRA src must be 4-byte aligned");
+    Guard guard(h->device);
+    cudaStream_t st = h->stream();
+    const int dw = sw * scale, dh = sh * scale;
+    Geometry g = make_geometry(sw, dh, scale);
+    if (int rc = h->uext.ensure(g.uext_frame * sizeof(float) * 4)) return rc;
+    if (int rc = h->hash.ensure(g.hash_frame)) return rc;
+    const size_t plane = (size_t)dw * dh;
+    const uint8_t* dsrc = src;
+    void* outs[4] = {hash, angle, l1, coherence};
+    void* dev[4] = {hash, angle, l1, coherence};
+    if (where == RAISR_HOST) {
+        if (int rc = h->dsrc[0].ensure(src_pitch * sh)) return rc;
+        if (int rc = h->dbg.ensure(plane * 4 * 4)) return rc;
+        CUDA_TRY(copy_rows(h->dsrc[0].p, src, src_pitch, (size_t)sw * 4, (size_t)sh, cudaMemcpyHostToDevice, st));
+        dsrc = (const uint8_t*)h->dsrc[0].p;
+        for (int i = 0; i < 4; ++i) dev[i] = outs[i] ? (char*)h->dbg.p + plane * 4 * i : nullptr;
+    }
+    h->scratch_acquire(st);
+    ColorUpParams cu{};
+    cu.src = dsrc; cu.src_pitch = src_pitch;
+    cu.sw = sw; cu.sh = sh; cu.dw = dw; cu.dh = dh; cu.pitch = g.uext_pitch;
+    for (int k = 0; k < 4; ++k) cu.plane[k] = (float*)h->uext.p + g.uext_frame * k;
+    dim3 gu((dw + 2 * kMargin + 255) / 256, (dh + 2 * kMargin + 3) / 4);
+    color_upscale_kernel<<<gu, 256, 0, st>>>(cu);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    PrepParams pp;
+    FilterParams fp;
+    fill_params(h, g, dsrc, sw, sh, src_pitch, nullptr, 0, scale, 0, 1, (float*)h->uext.p, (uint8_t*)h->hash.p, pp, fp);
+    pp.uext_in = (const float*)h->uext.p;   // Y plane
+    pp.dbg_hash = (int32_t*)dev[0]; pp.dbg_angle = (float*)dev[1]; pp.dbg_l1 = (float*)dev[2]; pp.dbg_coh = (float*)dev[3];
+    pp.dbg_pitch = dw;
+    if (int rc = launch_prep(h, pp, scale, st, true)) return rc;
+    h->scratch_release(st);
+    if (where == RAISR_HOST) {
+        for (int i = 0; i < 4; ++i)
             if (outs[i]) CUDA_TRY(cudaMemcpyAsync(outs[i], dev[i], plane * 4, cudaMemcpyDeviceToHost, st));
     }
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -1258,6 +1076,7 @@ int raisr_upsample_band_u8(raisr_t* h, const uint8_t* src_rows_ptr, int sw, int 
     pp.hash_frame_stride = g.hash_frame;
     pp.n_angle = h->n_angle; pp.n_strength = h->n_strength; pp.n_coherence = h->n_coherence; pp.as_written = h->as_written; pp.cubic = h->cubic;
     memcpy(pp.sq, h->sq, sizeof(pp.sq)); memcpy(pp.cq, h->cq, sizeof(pp.cq));
+    h->scratch_acquire(st);
     if (int rc = launch_prep(h, pp, scale, st, false)) return rc;
     FilterParams fp{};
     fp.uext = pp.uext; fp.uext_pitch = g.uext_pitch; fp.uext_frame_stride = g.uext_frame;
@@ -1267,7 +1086,9 @@ int raisr_upsample_band_u8(raisr_t* h, const uint8_t* src_rows_ptr, int sw, int 
     fp.n_buckets = h->n_buckets;
     fp.dst = dst; fp.dst_pitch = dst_pitch; fp.dst_frame_stride = 0;
     fp.ow = sw; fp.oh = dst_rows / scale; fp.n_frames = 1;
-    return launch_filter<uint8_t>(h, fp, scale, st);
+    const int rc = launch_filter<uint8_t>(h, fp, scale, st);
+    h->scratch_release(st);
+    return rc;
 }
 
 int raisr_ipc_export(const void* dev_ptr, unsigned char handle_out[64])

@@ -21,6 +21,9 @@ constexpr int kTaps = kFlen * kFlen;
 constexpr int kRowPad = 12;                    // floats per padded filter row
 constexpr int kFStride = kFlen * kRowPad;      // 132 floats per filter (33 x 16 B: odd -> banks spread)
 
+// tap formats of the table slice resident in shared memory (raisr_octet.cuh)
+enum { kTapsF32 = 0, kTapsF16 = 1, kTapsB24 = 2 };
+
 struct FilterParams {
     const float* uext;        // (own_rows*S + 10) rows per frame, column-major, see raisr_prep.cuh
     size_t uext_pitch;        // floats per image column

@@ -16,7 +16,9 @@
 // values per run and pixel), and eight pixels' partial sums are combined with a 7-shuffle
 // transposing butterfly.
 #pragma once
+#include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -74,6 +76,80 @@ inline void octet_pack_filter_h16(const float* f, uint16_t* rec, int S, ToHalf t
             rec[(p + 8 * (slot / 8)) * 8 + slot % 8] = to_half(tmp[(p + 8 * (slot / 4)) * 4 + slot % 4]);
 }
 
+// 24-bit tap records ("taps_b24"): every tap keeps its sign, its 8 exponent bits and the top 15 mantissa bits
+// (3 bytes instead of 4), which cuts the shared-memory tap stream -- the resource that bounds this kernel -- by
+// a quarter.  A lane's 16 taps form a circular stream of 48 bytes = three 16-byte chunks; tap k owns stream
+// bytes 3k+1 .. 3k+3 (mod 48, most significant last) and is used as the little-endian 32-bit word that starts at
+// byte 3k: its low byte is the top byte of tap k-1, a known value, so the packer picks the 24 own bits that make
+// the WHOLE word the float nearest to the original tap (|error| <= 2^-16 relative, half of plain truncation's
+// worst case) and the kernel needs one PRMT per tap (none for taps 0, 4, 8, 12, which are word-aligned).
+// Record = 24 chunks = 384 B; lane p reads chunks p, p+8, p+16: conflict-free like the fp32 record.
+constexpr int kOctBytesB24 = 384;
+
+inline float b24_word_to_float(uint32_t w)
+{
+    float f;
+    memcpy(&f, &w, 4);
+    return f;
+}
+
+// Encodes 16 slot values into the 48-byte circular stream; `eff` receives the values the kernel will decode.
+inline void b24_encode_lane(const float v[16], uint8_t stream[48], float eff[16])
+{
+    uint32_t bits[16], own[16];   // own = the 24 stored bits (sign, exponent, 15 mantissa bits)
+    for (int k = 0; k < 16; ++k) { memcpy(&bits[k], &v[k], 4); own[k] = bits[k] >> 8; }
+    for (int pass = 0; pass < 4; ++pass) {
+        bool changed = false;
+        for (int k = 0; k < 16; ++k) {
+            const uint32_t g = own[(k + 15) & 15] >> 16;                 // low byte of the word: top byte of tap k-1
+            const uint32_t sign = bits[k] & 0x80000000u, mag = bits[k] & 0x7fffffffu;
+            uint32_t best = own[k];
+            double best_err = 1e300;
+            for (int d = -1; d <= 1; ++d) {
+                const long long hm = (long long)(mag >> 8) + d;
+                if (hm < 0 || hm > 0x7f7fff) continue;                   // stay finite
+                const uint32_t w = sign | ((uint32_t)hm << 8) | g;
+                const double err = fabs((double)b24_word_to_float(w) - (double)v[k]);
+                if (err < best_err) { best_err = err; best = w >> 8; }
+            }
+            if (best != own[k]) { own[k] = best; changed = true; }
+        }
+        if (!changed) break;
+    }
+    for (int k = 0; k < 16; ++k) {
+        stream[(3 * k + 1) % 48] = (uint8_t)(own[k] & 0xff);
+        stream[(3 * k + 2) % 48] = (uint8_t)((own[k] >> 8) & 0xff);
+        stream[(3 * k + 3) % 48] = (uint8_t)(own[k] >> 16);
+    }
+    for (int k = 0; k < 16; ++k) {
+        const uint32_t w = (uint32_t)stream[3 * k] | ((uint32_t)stream[3 * k + 1] << 8) | ((uint32_t)stream[3 * k + 2] << 16) |
+                           ((uint32_t)stream[(3 * k + 3) % 48] << 24);
+        eff[k] = b24_word_to_float(w);
+    }
+}
+
+// Packs one 11x11 filter into a 384-byte b24 record; `eff` (121 floats, may be null) receives the tap values the
+// kernel will actually multiply by, in the reference's row-major order.
+inline void octet_pack_filter_b24(const float* f, uint8_t* rec, int S, float* eff)
+{
+    float slots[kOctStride], idx[kOctStride], fi[kTaps];
+    octet_pack_filter_s(f, slots, S);
+    for (int t = 0; t < kTaps; ++t) fi[t] = (float)(t + 1);
+    octet_pack_filter_s(fi, idx, S);                                     // which tap sits in which slot (0 = unused)
+    for (int p = 0; p < 8; ++p) {
+        float v[16], e[16];
+        uint8_t stream[48];
+        for (int sl = 0; sl < 16; ++sl) v[sl] = slots[(p + 8 * (sl / 4)) * 4 + sl % 4];
+        b24_encode_lane(v, stream, e);
+        for (int n = 0; n < 48; ++n) rec[(p + 8 * (n / 16)) * 16 + n % 16] = stream[n];
+        if (eff)
+            for (int sl = 0; sl < 16; ++sl) {
+                const int t = (int)idx[(p + 8 * (sl / 4)) * 4 + sl % 4];
+                if (t > 0) eff[t - 1] = e[sl];
+            }
+    }
+}
+
 template <int S>
 struct OctetCfg;
 // OTW x OTH own pixels per tile, one item of IW pixels per octet, NT threads.
@@ -113,11 +189,13 @@ struct OctetGeom {
     static_assert(ITEMS == NOCT && (S * C::OTH) % 4 == 0, "one item per octet and tile; tiles start on row quads");
 };
 
+__host__ __device__ constexpr int octet_record_bytes(int tf) { return tf == kTapsF16 ? kOctStrideH * 2 : tf == kTapsB24 ? kOctBytesB24 : kOctStride * 4; }
+
 template <int S, int NBUF = 2>
-inline size_t octet_smem_bytes(int n_buckets, bool h16 = false)
+inline size_t octet_smem_bytes(int n_buckets, int tf = kTapsF32)
 {
     using G = OctetGeom<S>;
-    const size_t rec = h16 ? kOctStrideH * 2 : kOctStride * sizeof(float);
+    const size_t rec = octet_record_bytes(tf);
     return (size_t)n_buckets * rec + NBUF * (size_t)G::BUF_BYTES + 32;   // + four mbarriers (full / empty per buffer)
 }
 
@@ -256,14 +334,17 @@ __device__ __forceinline__ void octet_issue_tile(const FilterParams& p, const CU
 // warp that arrives LAST -- at that point nobody reads the buffer any more -- issues the TMA of the tile after
 // next into it.  Warps wait only for the tile they need, so they drift apart and the shared-memory pipe no
 // longer drains at every tile boundary (filter 11.04 -> 10.4 ms per step).
-template <int S, typename OutT, int NBUF = 2, bool H16 = false, bool PIPE = false>
+// TF = kTapsB24: 384-byte records of 24-bit taps (see octet_pack_filter_b24): three predicated LDS.128 per lane and
+// pixel instead of four, twelve PRMT on the otherwise idle integer pipe, the same fp32 FMA chain.
+template <int S, typename OutT, int NBUF = 2, int TF = kTapsF32, bool PIPE = false>
 __global__ void __launch_bounds__(OctetCfg<S>::NT, 1)
     filter_octet_kernel(const FilterParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap hmap)
 {
     static_assert(!PIPE || NBUF == 2, "the pipelined kernel is double-buffered");
     using C = OctetCfg<S>;
     using G = OctetGeom<S>;
-    constexpr int REC = H16 ? kOctStrideH * 2 : kOctStride * 4;      // bytes per filter record
+    constexpr bool H16 = TF == kTapsF16, B24 = TF == kTapsB24;
+    constexpr int REC = octet_record_bytes(TF);                      // bytes per filter record
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* tab = reinterpret_cast<float*>(smem_raw);                 // 128-B aligned records
     unsigned char* buf0 = smem_raw + (size_t)p.n_buckets * REC;
@@ -376,8 +457,10 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1)
             unsigned bucket = min(hb.x & 0xffu, maxb);
             const float4* tp = tab_lane + bucket * (REC / 16);
             float4 t0 = {}, t1 = {}, t2 = {}, t3 = {};
-            uint4 q0 = {}, q1 = {};
-            if (H16) {
+            uint4 q0 = {}, q1 = {}, q2 = {};
+            if (B24) {
+                q0 = *reinterpret_cast<const uint4*>(tp); q1 = *reinterpret_cast<const uint4*>(tp + 8); q2 = *reinterpret_cast<const uint4*>(tp + 16);
+            } else if (H16) {
                 q0 = *reinterpret_cast<const uint4*>(tp); q1 = *reinterpret_cast<const uint4*>(tp + 8);
             } else {
                 t0 = tp[0]; t1 = tp[8]; t2 = tp[16]; t3 = tp[24];
@@ -399,7 +482,27 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1)
                     constexpr int MP = G::WP - 1;
                     const int o = S * b;
                     float a0, a1;
-                    if (H16) {
+                    if (B24) {
+                        // tap k = the 32-bit word at stream byte 3k (see octet_pack_filter_b24)
+                        auto W = [](unsigned lo, unsigned hi, unsigned sel) { return __uint_as_float(__byte_perm(lo, hi, sel)); };
+                        const float c15 = W(q2.w, q0.x, 0x4321);
+                        const float c0 = __uint_as_float(q0.x), c1 = W(q0.x, q0.y, 0x6543), c2 = W(q0.y, q0.z, 0x5432), c3 = W(q0.z, q0.w, 0x4321);
+                        const float c4 = __uint_as_float(q0.w), c5 = W(q0.w, q1.x, 0x6543);
+                        lds128_if(q0, tpa, reload);
+                        const float c6 = W(q1.x, q1.y, 0x5432), c7 = W(q1.y, q1.z, 0x4321);
+                        const float c8 = __uint_as_float(q1.z), c9 = W(q1.z, q1.w, 0x6543), c10 = W(q1.w, q2.x, 0x5432);
+                        lds128_if(q1, tpa + 128, reload);
+                        const float c11 = W(q2.x, q2.y, 0x4321), c12 = __uint_as_float(q2.y), c13 = W(q2.y, q2.z, 0x6543), c14 = W(q2.z, q2.w, 0x5432);
+                        lds128_if(q2, tpa + 256, reload);
+                        a0 = w11[(o + 0) % G::WF] * c0; a1 = w11[(o + 1) % G::WF] * c1;
+                        a0 = fmaf(w11[(o + 2) % G::WF], c2, a0); a1 = fmaf(w11[(o + 3) % G::WF], c3, a1);
+                        a0 = fmaf(w11[(o + 4) % G::WF], c4, a0); a1 = fmaf(w11[(o + 5) % G::WF], c5, a1);
+                        a0 = fmaf(w11[(o + 6) % G::WF], c6, a0); a1 = fmaf(w11[(o + 7) % G::WF], c7, a1);
+                        a0 = fmaf(w11[(o + 8) % G::WF], c8, a0); a1 = fmaf(w11[(o + 9) % G::WF], c9, a1);
+                        a0 = fmaf(w11[(o + 10) % G::WF], c10, a0); a1 = fmaf(w5[(o + 0) & MP], c11, a1);
+                        a0 = fmaf(w5[(o + 1) & MP], c12, a0); a1 = fmaf(w5[(o + 2) & MP], c13, a1);
+                        a0 = fmaf(w5[(o + 3) & MP], c14, a0); a1 = fmaf(w5[(o + 4) & MP], c15, a1);
+                    } else if (H16) {
                         float2 c0 = h2f2(q0.x), c1 = h2f2(q0.y), c2 = h2f2(q0.z), c3 = h2f2(q0.w);
                         lds128_if(q0, tpa, reload);
                         a0 = w11[(o + 0) % G::WF] * c0.x; a1 = w11[(o + 1) % G::WF] * c0.y;

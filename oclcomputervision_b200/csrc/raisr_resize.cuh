@@ -51,7 +51,7 @@ constexpr int kResizeWin = 10240;             // floats of decoded source window
 template <int CH>
 __global__ void __launch_bounds__(256) resize_kernel(const ResizeParams p)
 {
-    __shared__ float win[kResizeWin];
+    __shared__ __align__(16) float win[kResizeWin];
     __shared__ float lut[256];
     __shared__ int rowoff[kResizeRows][4];      // clamped source row indices (2 used by the bilinear modes)
     __shared__ float roww[kResizeRows][4];      // bilinear: (1-v, v); bicubic: the four y weights

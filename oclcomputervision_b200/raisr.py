@@ -44,6 +44,8 @@ class ClRaisr:
     sobelX = np.array([-1, 0, 1, -2, 0, 2, -1, 0, 1], dtype=np.float32)
     sobelY = np.array([-1, -2, -1, 0, 0, 0, 1, 2, 1], dtype=np.float32)
 
+    _TAPS = {"fp32": 0, "fp16": 1, "b24": 2, "auto": 3}
+
     def gaussian2d(self, shape=(3, 3), sigma=0.5):
         """Normalised 2-D Gaussian mask, MATLAB fspecial('gaussian') convention (same result as raisr.py:48-60)."""
         half_r, half_c = (float(shape[0]) - 1.0) / 2.0, (float(shape[1]) - 1.0) / 2.0
@@ -56,15 +58,17 @@ class ClRaisr:
 
     def __init__(self, grayMode, filters: Optional[np.ndarray] = None, device: int = 0,
                  n_angle: int = 24, n_strength: int = 3, n_coherence: int = 3,
-                 filter_path: Optional[str] = None, quirks: str = "intended", taps: str = "fp32",
+                 filter_path: Optional[str] = None, quirks: str = "intended", taps: str = "auto",
                  upscaler: str = "bilinear"):
-        """quirks="as_written" reproduces the three slips of the kernel text (raisr.cl:271,310,316);
-        taps="fp16" rounds every tap to half precision like the reference's `(half)pf[...]` (raisr.cl:328).
-        Both default to the intended fp32 algorithm; arithmetic is fp32 in every mode."""
+        """quirks="as_written" reproduces the three slips of the kernel text (raisr.cl:271,310,316).
+        taps = precision of the taps held in shared memory (arithmetic is fp32 in every mode): "fp32"; "fp16" =
+        rounded to half precision like the reference's `(half)pf[...]` (raisr.cl:328); "b24" = sign, exponent and 15
+        mantissa bits; "auto" (default) = b24 when that provably keeps every output within 5e-5 of the fp32-tap
+        result (`effective_filters()` reports the bound), else fp32."""
         if grayMode not in (0, 1):
             raise ValueError("grayMode must be 1 (gray, raisr.py:97-100) or 0 (BGRA, raisr.py:101-104)")
-        if quirks not in ("intended", "as_written") or taps not in ("fp32", "fp16") or upscaler not in ("bilinear", "bicubic"):
-            raise ValueError("quirks must be 'intended' or 'as_written', taps 'fp32' or 'fp16', upscaler 'bilinear' or 'bicubic'")
+        if quirks not in ("intended", "as_written") or taps not in self._TAPS or upscaler not in ("bilinear", "bicubic"):
+            raise ValueError("quirks must be 'intended' or 'as_written', taps one of %s, upscaler 'bilinear' or 'bicubic'" % sorted(self._TAPS))
         self.grayMode = grayMode
         self.n_angle, self.n_strength, self.n_coherence = n_angle, n_strength, n_coherence
         self._lib = _cabi.load()
@@ -74,8 +78,8 @@ class ClRaisr:
         self.quirks, self.taps = quirks, taps
         if quirks == "as_written":
             self.set_option("quirks", 1)
-        if taps == "fp16":
-            self.set_option("taps_fp16", 1)
+        if taps != "auto":
+            self.set_option("taps", self._TAPS[taps])
         if upscaler == "bicubic":   # the reference's unused cubic_sample as stage 1 (raisr.cl:63-106)
             self.set_option("cheap_upscaler", 1)
         # raisr.py:80-82
@@ -83,10 +87,16 @@ class ClRaisr:
         g = np.diag(g.ravel()).astype(np.float32)
         self.gaussian = np.diag(g).copy()
         if filters is None:
-            path = filter_path or os.path.join(os.getcwd(), "filter.p")
-            if os.path.exists(path):  # raisr.py:77-78
+            # raisr.py:74-78 unpickles `filter.p` from the module's own directory; so does this class (never the
+            # process's working directory).  A pickle executes code when loaded: only point filter_path at files
+            # you trust -- pass `filters=` (a plain array) otherwise.
+            path = filter_path or os.path.join(os.path.dirname(os.path.abspath(__file__)), "filter.p")
+            if os.path.exists(path):
                 with open(path, "rb") as fp:
                     filters = pickle.load(fp)
+            elif filter_path is not None:
+                self.close()
+                raise FileNotFoundError(filter_path)
         if filters is not None:
             self.filters_x2 = filters
 
@@ -102,6 +112,14 @@ class ClRaisr:
     filters_x2 = property(lambda self: self._filters.get(2), lambda self, t: self._set_filters(2, t))
     filters_x3 = property(lambda self: self._filters.get(3), lambda self, t: self._set_filters(3, t))
     filters_x4 = property(lambda self: self._filters.get(4), lambda self, t: self._set_filters(4, t))
+
+    def effective_filters(self, scale: int):
+        """(table, tap_format, b24_bound): the taps the gray filter kernel actually multiplies by (reference layout),
+        the format in use ("fp32" | "fp16" | "b24") and the bound on |output - fp32-tap output| of the b24 records."""
+        t = np.empty_like(self._filters[scale])
+        fmt, bound = ctypes.c_int(), ctypes.c_float()
+        _cabi.check(self._lib.raisr_get_effective_filters(self._h, scale, t.ctypes.data, t.size, ctypes.byref(fmt), ctypes.byref(bound)))
+        return t, ("fp32", "fp16", "b24")[fmt.value], float(bound.value)
 
     def set_quantizers(self, strength_q: Sequence[float], coherence_q: Sequence[float]) -> None:
         """Thresholds of raisr.py:112-115."""
@@ -200,6 +218,13 @@ class ClRaisr:
         dh, dw = src.shape[0] * scale_factor, src.shape[1] * scale_factor
         h = np.empty((dh, dw), np.int32)
         a, l1, co, u = (np.empty((dh, dw), np.float32) for _ in range(4))
+        if self.grayMode == 0:   # colour: the quantities come from the Y plane; there is no single upscaled image
+            if src.ndim != 3 or src.shape[2] != 4:
+                raise ValueError("colour mode expects (h, w, 4) BGRA arrays")
+            _cabi.check(self._lib.raisr_debug_hash_bgra(self._h, src.ctypes.data, src.shape[1], src.shape[0], src.strides[0],
+                                                        int(scale_factor), h.ctypes.data, a.ctypes.data, l1.ctypes.data,
+                                                        co.ctypes.data, _cabi.RAISR_HOST))
+            return h, a, l1, co, None
         _cabi.check(self._lib.raisr_debug_hash(self._h, src.ctypes.data, src.shape[1], src.shape[0], src.strides[0],
                                                int(scale_factor), h.ctypes.data, a.ctypes.data, l1.ctypes.data,
                                                co.ctypes.data, u.ctypes.data, _cabi.RAISR_HOST))

@@ -289,8 +289,9 @@ def build_c(force: bool = False) -> str:
 def _load():
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
-            build_c()
+        src_c = os.path.join(_HERE, "raisr_oracle.c")
+        if not os.path.exists(_SO) or (os.path.exists(src_c) and os.path.getmtime(src_c) > os.path.getmtime(_SO)):
+            build_c(force=True)
         lib = ctypes.CDLL(_SO)
         vp = ctypes.c_void_p
         lib.raisr_oracle_run.restype = ctypes.c_int
@@ -306,6 +307,8 @@ def _load():
         lib.raisr_oracle_run_bgra.restype = ctypes.c_int
         lib.raisr_oracle_run_bgra.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_int, vp, ctypes.c_int,
                                               ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int]
+        lib.raisr_oracle_run_bgra_ex.restype = ctypes.c_int
+        lib.raisr_oracle_run_bgra_ex.argtypes = list(lib.raisr_oracle_run_bgra.argtypes) + [vp, vp, vp]
         lib.raisr_oracle_resize_u8.restype = ctypes.c_int
         lib.raisr_oracle_resize_u8.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_int, vp,
                                                ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_int]
@@ -399,10 +402,12 @@ def raisr_ref_bgra_c(src_bgra: np.ndarray, filters: np.ndarray, s: int = 2, *, n
     flt = np.ascontiguousarray(filters, dtype=F32)
     sq = np.ascontiguousarray(strength_q, dtype=F32)
     cq = np.ascontiguousarray(coherence_q, dtype=F32)
-    res = dict(hash=np.empty((dh, dw), np.int32), out_f32=np.empty((dh, dw, 4), F32), out_u8=np.empty((dh, dw, 4), np.uint8))
-    rc = lib.raisr_oracle_run_bgra(src.ctypes.data, sw, sh, src.strides[0], s, flt.ctypes.data, n_angle, n_strength, n_coherence,
-                                   sq.ctypes.data, cq.ctypes.data, res["hash"].ctypes.data, res["out_f32"].ctypes.data,
-                                   res["out_u8"].ctypes.data, int(nthreads))
+    res = dict(hash=np.empty((dh, dw), np.int32), out_f32=np.empty((dh, dw, 4), F32), out_u8=np.empty((dh, dw, 4), np.uint8),
+               angle=np.empty((dh, dw), F32), L1=np.empty((dh, dw), F32), coherence=np.empty((dh, dw), F32))
+    rc = lib.raisr_oracle_run_bgra_ex(src.ctypes.data, sw, sh, src.strides[0], s, flt.ctypes.data, n_angle, n_strength, n_coherence,
+                                      sq.ctypes.data, cq.ctypes.data, res["hash"].ctypes.data, res["out_f32"].ctypes.data,
+                                      res["out_u8"].ctypes.data, int(nthreads), res["angle"].ctypes.data, res["L1"].ctypes.data,
+                                      res["coherence"].ctypes.data)
     if rc != 0:
         raise RuntimeError("raisr_oracle_run_bgra failed (%d)" % rc)
     return res

@@ -86,3 +86,49 @@ def test_filter_record_packing_covers_every_tap_once():
         for i in range(3):
             put(6 + i // newp, 16 - newp + i % newp, (8 + i) * 11 + 0)
         assert sorted(seen.values()) == list(range(121))
+
+
+def _decode_b24_record(rec: np.ndarray):
+    """Independent decode of a 384-byte record following the layout documented in include/raisr_b200.h:
+    lane p owns chunks p, p+8, p+16 (a circular 48-byte stream); slot k = little-endian u32 at stream byte 3k."""
+    out = np.zeros((8, 16), np.float32)
+    for p in range(8):
+        stream = np.concatenate([rec[(p + 8 * j) * 16:(p + 8 * j) * 16 + 16] for j in range(3)])
+        for k in range(16):
+            b = [int(stream[(3 * k + i) % 48]) for i in range(4)]
+            out[p, k] = np.array([b[0] | b[1] << 8 | b[2] << 16 | b[3] << 24], np.uint32).view(np.float32)[0]
+    return out
+
+
+@pytest.mark.parametrize("scale", [2, 3, 4])
+def test_b24_tap_records_round_to_within_2_pow_minus_16(scale):
+    """The 24-bit tap records (raisr_pack_taps_b24, csrc/raisr_octet.cuh): every tap of the filter appears exactly
+    once among the decoded slots, its decoded value is what the packer reports as `effective`, and it is within
+    2^-16 relative of the fp32 tap (sign + exponent + 15 mantissa bits, low byte chosen jointly)."""
+    lib = _cabi.load()
+    rng = np.random.default_rng(scale)
+    for trial in range(20):
+        f = rng.normal(0, 0.02, 121).astype(np.float32)
+        f[60] += 1
+        if trial == 1:
+            f[:] = 0
+        if trial == 2:
+            f = (rng.standard_normal(121) * 10.0 ** rng.integers(-20, 20, 121)).astype(np.float32)
+        if trial == 3:
+            f[::2] = np.float32(1.9999999)      # mantissa all ones: rounding carries into the exponent
+        rec = np.zeros(384, np.uint8)
+        eff = np.full(121, np.nan, np.float32)
+        assert lib.raisr_pack_taps_b24(f.ctypes.data, scale, rec.ctypes.data, eff.ctypes.data) == 0
+        assert np.isfinite(eff).all()
+        tol = np.abs(f).astype(np.float64) * 2.0 ** -16 + 1e-40
+        assert (np.abs(eff.astype(np.float64) - f) <= tol).all()
+        slots = _decode_b24_record(rec).ravel()
+        # every effective tap is among the decoded slot values; the unused slots decode to (sub)normal dust
+        used = np.zeros(slots.size, bool)
+        for t in range(121):
+            hit = np.flatnonzero((slots.view(np.uint32) == eff[t:t + 1].view(np.uint32)[0]) & ~used)
+            assert hit.size >= 1, t
+            used[hit[0]] = True
+        assert (np.abs(slots[~used]) < 1e-35).all()
+    assert lib.raisr_pack_taps_b24(None, scale, rec.ctypes.data, eff.ctypes.data) == _cabi.E_ARG
+    assert lib.raisr_pack_taps_b24(f.ctypes.data, 5, rec.ctypes.data, eff.ctypes.data) == _cabi.E_UNSUPPORTED

@@ -31,7 +31,14 @@ def raisr():
     r.close()
 
 
-def check_against_oracle(raisr, src, s, F, impl=None):
+TOL_EFF = 5e-6   # against the oracle run on the taps the kernel actually holds (summation order differs, nothing else)
+
+
+def check_against_oracle(raisr, src, s, F, impl=None, label=""):
+    """Full-frame comparison with the C oracle.  Returns dict(excused, unexcused, err_fp32, err_eff, tap_format, bound).
+    Hash mismatches are classified by the oracle's distance to the nearest bin edge (< 1e-5 = excused); pixels are
+    compared (i) with the fp32-tap oracle at the north_star tolerance of 1e-4 / 1 LSB and (ii) with the oracle run
+    on `effective_filters()` -- the 24-bit taps when the table qualifies -- at 5e-6."""
     ref = O.raisr_ref_c(src, F, s)
     if impl is not None:
         raisr.set_option("filter_impl", impl)
@@ -42,7 +49,7 @@ def check_against_oracle(raisr, src, s, F, impl=None):
     diff = h != ref["hash"]
     excused = diff & (O.edge_distance(ref) < EDGE_EPS)
     unexcused = int((diff & ~excused).sum())
-    print("hash mismatches: %d excused (bin edge), %d unexcused, of %d" % (int(excused.sum()), unexcused, h.size))
+    print("%shash mismatches: %d excused (bin edge), %d unexcused, of %d" % (label, int(excused.sum()), unexcused, h.size))
     assert unexcused == 0
     out = raisr.upsample_f32(src, s)
     dst = np.zeros((src.shape[0] * s, src.shape[1] * s), np.uint8)
@@ -51,8 +58,21 @@ def check_against_oracle(raisr, src, s, F, impl=None):
     ok = ~diff  # pixels that hashed to a different (edge) bucket legitimately use another filter
     err = np.abs(out - ref["out_f32"])
     assert err[ok].max() < TOL_F32, err[ok].max()
-    assert np.abs(dst.astype(int) - ref["out_u8"].astype(int))[ok].max() <= 1
-    return float(err[ok].max())
+    lsb = np.abs(dst.astype(int) - ref["out_u8"].astype(int))
+    assert lsb[ok].max() <= 1
+    Feff, fmt, bound = raisr.effective_filters(s)
+    err_eff = float(err[ok].max())
+    if fmt != "fp32" and impl != 0:      # the block kernel (impl 0) always holds fp32 taps
+        assert bound <= 5e-5 or raisr.taps != "auto"
+        assert np.abs(Feff - F).max() <= np.abs(F).max() * 2.0 ** -16
+        ref_eff = O.raisr_ref_c(src, Feff, s, want=("out_f32",))
+        err_eff = float(np.abs(out - ref_eff["out_f32"])[ok].max())
+        assert err_eff < TOL_EFF, err_eff
+        assert err[ok].max() <= bound + TOL_EFF
+    print("%smax |out - oracle(fp32 taps)| = %.3g, vs oracle(%s taps) = %.3g, b24 bound %.3g, u8 > 0 LSB on %d px" %
+          (label, float(err[ok].max()), fmt, err_eff, bound, int((lsb[ok] > 0).sum())))
+    return dict(excused=int(excused.sum()), unexcused=unexcused, err_fp32=float(err[ok].max()), err_eff=err_eff,
+                tap_format=fmt, bound=bound)
 
 
 @pytest.mark.parametrize("impl", [1, 0])
@@ -91,7 +111,7 @@ def test_lenna_config1(raisr, golden_dir):
     # BASELINE.json configs[0]: 512x512 luma of images/lenna.png, 2x, 24x3x3x4 buckets
     g = np.load(os.path.join(golden_dir, "lenna_x2.npz"))
     src = g["src"]
-    err = check_against_oracle(raisr, src, 2, raisr.filters_x2, 1)
+    err = check_against_oracle(raisr, src, 2, raisr.filters_x2, 1)["err_fp32"]
     h = raisr.debug_hash(src, 2)[0]
     hist = np.bincount(h.ravel(), minlength=864)
     assert np.abs(hist - g["hash_hist"]).sum() <= 40         # only bin-edge pixels may move (2 entries each)
@@ -255,7 +275,7 @@ def test_quirks_and_fp16_taps_against_oracle(quirks, taps, scale):
     r.upsample(src, dst, scale)
     assert np.abs(dst.astype(int) - want["out_u8"].astype(int))[ok].max() <= 1
     # switching the tap precision back re-packs the table
-    r.set_option("taps_fp16", 0)
+    r.set_option("taps", 0)
     r.set_option("quirks", 0)
     assert np.abs(r.upsample_f32(src, scale) - base["out_f32"])[r.debug_hash(src, scale)[0] == base["hash"]].max() <= 1e-4
 
