@@ -1,22 +1,33 @@
 #!/usr/bin/env python
 """bench.py -- RAISR 2x output Mpix/s on B200 (BASELINE.json metric), one JSON line on stdout.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 3|2|5] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one pass of the hot path over one batch: BASELINE.json configs[1], 64 synthetic 1080p
-luma frames -> 4K (u8 in, u8 out) per GPU.  With N GPUs every rank processes its own 64 frames
-(frames are independent, no collective: weak scaling); `value` is the whole-job output Mpix/s.
+A "step" is one pass of the hot path over one batch of synthetic luma frames (u8 in, u8 out).  The default workload
+is the size north_star quotes its target on, BASELINE.json configs[2]: 4K -> 8K, 16 frames per GPU per step
+(`--config 2` = configs[1], 1080p -> 4K x 64 frames; `--config 5` = configs[4], 720p x 256 frames).  With N GPUs every
+rank processes its own frames (frames are independent, no collective: weak scaling); `value` is the whole-job
+output Mpix/s.
 
   value      device-resident throughput (inputs already in HBM), CUDA events, max over ranks
-  e2e        same metric through the C-ABI with HOST (pinned) buffers: H2D and D2H inside the call
-  roofline   FP32-FFMA roofline of SURVEY.md 8(d): 412 algorithmic FLOP per output pixel over the
-             summed kernel time of the step, against 2*128*SMs*max_clock and the measured FFMA peak
-  cpu_baseline  the oracle's C port (oracle/raisr_oracle.c) on the host cores of this box -- the
-             reference has no CPU RAISR path and its OpenCL path cannot run
+  e2e        same metric through the C-ABI with HOST (pinned) buffers: H2D and D2H inside the call; next to it the
+             raw copy ceiling of the box (the same bytes moved by bare cudaMemcpyAsync, all ranks at once)
+  roofline   FP32-FFMA roofline of SURVEY.md 8(d): 412 algorithmic FLOP per output pixel over the summed kernel
+             time of the step (CUDA events around every launch, on the launch stream), against 2*128*SMs*max_clock and
+             a measured register-only FFMA kernel; ncu-derived figures are read from profiles/ncu_kernel_metrics.json
+             (with the capture they come from), never hard-coded
+  variants   the same step with fp32 and fp16 tap records (the default is "auto" -> 24-bit records), with each
+             variant's maximum output deviation from the fp32-tap result
+  band       BASELINE.json configs[3]: one 16384x16384 image, 3x, row-banded over the N ranks with the halo rows
+             read from the neighbour's memory over NVLink; device ms, Gpix/s, halo bytes, output checksum
+  next_rows  the byte-stream kernels of SURVEY.md 8(f) against the HBM roofline (N = 1 only)
+  cpu_baseline  the oracle's C port (oracle/raisr_oracle.c) on the host cores of this box -- the reference has no CPU
+             RAISR path and its OpenCL path cannot run
 `--impl reference` times that CPU port alone (there is nothing else of the reference to time).
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -30,41 +41,55 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SW, SH, SCALE, FRAMES = 1920, 1080, 2, 64       # BASELINE.json configs[1]
+SCALE = 2
+CONFIGS = {   # BASELINE.json config number (1-based) -> source size, frames per GPU per step
+    2: dict(sw=1920, sh=1080, frames=64, name="1080p->4K", baseline="configs[1]"),
+    3: dict(sw=3840, sh=2160, frames=16, name="4K->8K", baseline="configs[2] (north_star target size; 16 of its 512 frames per GPU per step)"),
+    5: dict(sw=1280, sh=720, frames=256, name="720p->1440p", baseline="configs[4] (256 of its 2048 frames per GPU per step)"),
+}
 FLOP_PER_PX = 412.0                             # SURVEY.md 8(d), minimal form: whole path
 FLOP_PER_PX_FILTER = 244.0                      # 121 FMA + store: the dominant kernel's share of the 412
 BYTES_PER_PX = 1.0 / (SCALE * SCALE) + 1.0      # u8 in -> u8 out
-# From the committed ncu capture of this command's kernels (profiles/r1i_ncu_summary.txt):
-NCU_FILTER_WAVEFRONTS_PER_PX = 4.915            # l1tex__data_pipe_lsu_wavefronts_mem_shared.sum / output pixels
-NCU_FILTER_DRAM_BYTES_PER_PX = 5.876            # dram__bytes_read.sum + dram__bytes_write.sum, per output pixel
 
 
-def make_inputs(n_frames, rank):
+def make_inputs(cfg, n_frames, rank):
     from oclcomputervision_b200 import synth
-    pool = synth.synthetic_batch(8, SH, SW, pool=8, seed=1000 + 16 * rank)
-    reps = (n_frames + 7) // 8
-    return np.ascontiguousarray(np.tile(pool, (reps, 1, 1))[:n_frames])
+    pool = min(4, n_frames)
+    frames = synth.synthetic_batch(pool, cfg["sh"], cfg["sw"], pool=pool, seed=1000 + 16 * rank)
+    reps = (n_frames + pool - 1) // pool
+    return np.ascontiguousarray(np.tile(frames, (reps, 1, 1))[:n_frames])
 
 
-def cpu_baseline(budget_s=12.0):
-    """C oracle on all host threads, bounded sample of the bench workload."""
+def cpu_oracle_rate(cfg, budget_s, steps=1, warm=0):
+    """C oracle on all host threads over a bounded sample of the workload; returns (Mpix/s, threads, frames per step, seconds)."""
     from oracle import raisr_oracle as O
     from oclcomputervision_b200 import synth
+    sw, sh = cfg["sw"], cfg["sh"]
     F = synth.random_filters(SCALE)
-    frame = synth.synthetic_frame(SH, SW, 1000)
+    frame = synth.synthetic_frame(sh, sw, 1000)
     threads = len(os.sched_getaffinity(0))   # torchrun exports OMP_NUM_THREADS=1; the oracle sets its own count
     t0 = time.perf_counter()
     O.raisr_ref_c(frame, F, SCALE, nthreads=threads, want=("out_u8",))
     one = time.perf_counter() - t0
     n = int(max(1, min(64, budget_s / max(one, 1e-3))))
+
+    def step():
+        for _ in range(n):
+            O.raisr_ref_c(frame, F, SCALE, nthreads=threads, want=("out_u8",))
+    for _ in range(warm):
+        step()
     t0 = time.perf_counter()
-    for k in range(n):
-        O.raisr_ref_c(frame, F, SCALE, nthreads=threads, want=("out_u8",))
+    for _ in range(steps):
+        step()
     dt = time.perf_counter() - t0
-    mpix = n * SW * SH * SCALE * SCALE / dt / 1e6
+    return steps * n * sw * sh * SCALE * SCALE / dt / 1e6, threads, n, dt
+
+
+def cpu_baseline(cfg, budget_s=12.0):
+    mpix, threads, n, dt = cpu_oracle_rate(cfg, budget_s)
     return dict(value=round(mpix, 3), unit="Mpix/s", cores=threads, kind="port",
-                sample="%d frame(s) of the %dx%d->%dx%d workload, C oracle (fp32, OpenMP), %.1f s" %
-                       (n, SW, SH, SW * SCALE, SH * SCALE, dt))
+                sample="%d frame(s) of the %s workload (%dx%d source), C oracle (fp32, OpenMP), %.1f s" %
+                       (n, cfg["name"], cfg["sw"], cfg["sh"], dt))
 
 
 class ClockSampler:
@@ -173,47 +198,180 @@ def bind_to_gpu_numa_node(index):
         return "unavailable: %s" % type(e).__name__
 
 
-def run_reference(args, rank, world):
+def workload_text(cfg, n, note=""):
+    return ("RAISR 2x %s luma u8->u8, batch of %d synthetic frames per GPU per step, random-init 24x3x3x4x121 table "
+            "(BASELINE %s)%s" % (cfg["name"], n, cfg["baseline"], note))
+
+
+def run_reference(args, cfg, rank, world):
     """Reference arm: the reference has no CPU RAISR path and its OpenCL kernel cannot run here, so this times the
     oracle's C port of raisr.cl on all host threads.  One step = a bounded sample of the bench workload (as many
-    1080p->4K frames as fit ~2 s); W warm-up steps, K timed steps."""
+    frames as fit ~2 s); W warm-up steps, K timed steps."""
     if rank != 0:
         return
-    from oracle import raisr_oracle as O
-    from oclcomputervision_b200 import synth
-    F = synth.random_filters(SCALE)
-    frame = synth.synthetic_frame(SH, SW, 1000)
-    threads = len(os.sched_getaffinity(0))
-    t0 = time.perf_counter()
-    O.raisr_ref_c(frame, F, SCALE, nthreads=threads, want=("out_u8",))
-    one = time.perf_counter() - t0
     steps, warm = max(1, args.steps), max(0, args.warmup)
     step_budget = min(2.0, 150.0 / (steps + warm))
-    n = int(max(1, min(64, step_budget / max(one, 1e-3))))
-
-    def step():
-        for _ in range(n):
-            O.raisr_ref_c(frame, F, SCALE, nthreads=threads, want=("out_u8",))
-    for _ in range(warm):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = time.perf_counter() - t0
-    mpix = steps * n * SW * SH * SCALE * SCALE / dt / 1e6
+    mpix, threads, n, dt = cpu_oracle_rate(cfg, step_budget, steps, warm)
     cb = dict(value=round(mpix, 3), unit="Mpix/s", cores=threads, kind="port",
-              sample="%d step(s) of %d frame(s) of the %dx%d->%dx%d workload, C oracle (fp32, OpenMP), %.1f s" %
-                     (steps, n, SW, SH, SW * SCALE, SH * SCALE, dt))
+              sample="%d step(s) of %d frame(s) of the %s workload (%dx%d source), C oracle (fp32, OpenMP), %.1f s" %
+                     (steps, n, cfg["name"], cfg["sw"], cfg["sh"], dt))
     line = dict(metric="RAISR 2x output Mpix/s", value=cb["value"], unit="Mpix/s", impl="reference",
                 n_gpus=args.gpus, steps=steps, warmup=warm, ms_per_step=round(dt / steps * 1e3, 3),
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload="RAISR 2x 1080p->4K luma u8->u8, random-init 24x3x3x4x121 fp32 table (BASELINE configs[1]); "
-                                     "bounded sample: %d frame(s) per step" % n,
+                config=dict(workload=workload_text(cfg, n, "; bounded sample: %d frame(s) per step" % n),
                             note="the reference has no CPU RAISR path and its OpenCL kernel cannot run here; "
                                  "this is the oracle's C port of raisr.cl on the host cores"),
                 cpu_baseline=cb, gpu_launches=0,
                 e2e=dict(value=cb["value"], unit="Mpix/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
+
+
+def ncu_metrics(kernel, taps):
+    """Figures that only a profiler can give (shared-memory wavefronts, DRAM bytes), from the committed capture."""
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "ncu_kernel_metrics.json")))
+        return table.get("%s/%s" % (kernel, taps))
+    except Exception:
+        return None
+
+
+def copy_ceiling(torch, h2d_bytes, d2h_bytes, barrier, reps=3):
+    """The same bytes as one e2e step moved by bare cudaMemcpyAsync from / to pinned memory on two streams, every rank
+    at once: what the box's host links give without any kernel in the way.  Returns seconds per step (this rank)."""
+    hs = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
+    hd = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+    ds = torch.empty(h2d_bytes, dtype=torch.uint8, device="cuda")
+    dd = torch.empty(d2h_bytes, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def once():
+        with torch.cuda.stream(s1):
+            ds.copy_(hs, non_blocking=True)
+        with torch.cuda.stream(s2):
+            hd.copy_(dd, non_blocking=True)
+    once()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / reps
+
+
+def band_record(torch, dist, r, rank, world, local_rank):
+    """BASELINE.json configs[3]: 16384x16384 -> 49152x49152 (3x, nine pixel types), one image, row bands over the ranks,
+    halo rows read from the neighbours over NVLink P2P (multi_gpu.BandedUpscaler, C-ABI only)."""
+    from oclcomputervision_b200 import synth, _cabi
+    from oclcomputervision_b200 import multi_gpu as mg
+    lib = _cabi.load()
+    sw = sh = 16384
+    s = 3
+    r.filters_x3 = synth.random_filters(3)
+    tile = synth.synthetic_frame(2048, 2048, 4242)          # the image is this tile repeated 8 x 8: cheap and rank-independent
+    r.set_stream(0)
+    up = mg.BandedUpscaler(r, sw, sh, s)
+    me = up.me
+    own = me.own_last - me.own_first + 1
+    hsrc, hdst = ctypes.c_void_p(), ctypes.c_void_p()
+    _cabi.check(lib.raisr_host_alloc(ctypes.byref(hsrc), max(1, own) * sw))
+    _cabi.check(lib.raisr_host_alloc(ctypes.byref(hdst), max(1, me.dst_rows) * sw * s))
+    src = np.ctypeslib.as_array((ctypes.c_ubyte * (own * sw)).from_address(hsrc.value)).reshape(own, sw)
+    rows = (np.arange(me.own_first, me.own_last + 1) % 2048)
+    src[:] = np.tile(tile[rows], (1, 8))
+    out = np.ctypeslib.as_array((ctypes.c_ubyte * (me.dst_rows * sw * s)).from_address(hdst.value)).reshape(me.dst_rows, sw * s)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    # end to end once (H2D of the owned rows, halo, kernels, D2H), then device-resident repeats
+    up.enqueue(hsrc.value, sw, hdst.value, sw * s)
+    first = up.finish()
+    times = []
+    for _ in range(3):
+        barrier()
+        up.enqueue(0, 0, 0, 0)
+        t = up.finish()
+        times.append(t["halo"] + t["kernels"])
+    dev_ms = float(np.median(times))
+    barrier()
+    t0 = time.perf_counter()
+    up.enqueue(hsrc.value, sw, hdst.value, sw * s)
+    e2e = up.finish()
+    e2e_wall = time.perf_counter() - t0
+    # position-sensitive checksum of the whole output image, independent of how it was banded
+    grow = np.arange(me.dst_row0, me.dst_row0 + me.dst_rows, dtype=np.uint64) + np.uint64(1)
+    col = np.arange(sw * s, dtype=np.uint64) + np.uint64(1)
+    row_sums = out.sum(axis=1, dtype=np.uint64)
+    col_sums = out.sum(axis=0, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        c1 = int((row_sums * grow).sum(dtype=np.uint64)) & 0xFFFFFFFFFFFF
+        c2 = int((col_sums * col).sum(dtype=np.uint64)) & 0xFFFFFFFFFFFF
+    stats = torch.tensor([dev_ms, e2e["total"], e2e_wall * 1e3, first["total"]], device="cuda", dtype=torch.float64)
+    sums = torch.tensor([c1, c2, up.halo_bytes], device="cuda", dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    up.close()
+    lib.raisr_host_free(hsrc); lib.raisr_host_free(hdst)
+    px = (sw * s) * (sh * s)
+    dev_ms, e2e_ms, e2e_wall_ms, first_ms = [float(x) for x in stats.tolist()]
+    c1, c2, halo = [int(x) for x in sums.tolist()]
+    return dict(workload="RAISR 3x 16384x16384 -> 49152x49152 (BASELINE configs[3]), one image row-banded over %d rank(s)" % world,
+                bands=world, band_rows_out=me.dst_rows, halo_rows_per_side_max=max([b.halo_above for b in up.bands] + [b.halo_below for b in up.bands]),
+                halo_bytes=halo, halo_transport="cudaMemcpy2DAsync from the neighbour's IPC-mapped window (NVLink P2P), ordered by device flags; no collective",
+                device_ms=round(dev_ms, 3), device_gpix_s=round(px / dev_ms / 1e6, 2), device_timing="halo wait + halo copies + kernels, CUDA events on the stream, median of 3, max over ranks",
+                e2e_ms=round(e2e_ms, 3), e2e_gpix_s=round(px / e2e_ms / 1e6, 2), e2e_wall_ms=round(e2e_wall_ms, 3),
+                e2e_note="H2D of the owned source rows + halo + kernels + D2H of the band, pinned host memory, max over ranks",
+                roofline_frac=round(FLOP_PER_PX * px / (dev_ms * 1e-3) / 1e12 / (world * 74.45), 4),
+                checksum="%012x%012x" % (c1 & 0xFFFFFFFFFFFF, c2 & 0xFFFFFFFFFFFF),
+                checksum_note="sum over the whole output of byte*(row+1) and byte*(col+1), mod 2^48 per rank then summed: equal for every N")
+
+
+def next_rows_record(torch, lib, h, peak):
+    """SURVEY.md 8(f) byte-stream kernels against the HBM roofline: algorithmic bytes / median kernel time."""
+    from oclcomputervision_b200 import _cabi
+    out = {}
+    ms = (ctypes.c_float * 3)()
+    rng = np.random.default_rng(0)
+
+    def timed(fn, reps=10):
+        ts = []
+        for i in range(reps + 3):
+            _cabi.check(fn())
+            if i >= 3:
+                ts.append(ms[1])
+        return float(np.median(ts))
+    sw, sh, frames = 1920, 1080, 16
+    dw, dh = 2 * sw, 2 * sh
+    for ch in (1, 4):
+        src = torch.from_numpy(rng.integers(0, 256, (frames, sh, sw * ch), dtype=np.uint8)).cuda()
+        dst = torch.empty((frames, dh, dw * ch), dtype=torch.uint8, device="cuda")
+        for mode, name in ((0, "bilinear_lds"), (1, "bicubic")):
+            t = timed(lambda: lib.raisr_resize_u8(h, ctypes.c_void_p(src.data_ptr()), sw, sh, sw * ch, ch, ctypes.c_void_p(dst.data_ptr()),
+                                                  dw, dh, dw * ch, mode, frames, _cabi.RAISR_DEVICE, ms))
+            nbytes = frames * (sw * sh + dw * dh) * ch
+            out["resize_%s_%s" % (name, "gray" if ch == 1 else "bgra")] = dict(
+                ms=round(t, 4), out_gpix_s=round(frames * dw * dh / t / 1e6, 1), achieved_gbs=round(nbytes / t / 1e6, 1),
+                frac=round(nbytes / t / 1e6 / peak, 3))
+        del src, dst
+    n = 16384
+    img = torch.from_numpy(rng.integers(0, 256, (n, n), dtype=np.uint8)).cuda()
+    dst = torch.empty((n, n), dtype=torch.uint8, device="cuda")
+    nx = ny = n // 256
+    hist = torch.empty((n // 32, nx, 256), dtype=torch.int32, device="cuda")
+    maps = torch.from_numpy((rng.random((ny, nx, 256)) * 255).astype(np.float32)).cuda()
+    lut = torch.from_numpy(rng.permutation(256).astype(np.uint8)).cuda()
+    P = lambda t_: ctypes.c_void_p(t_.data_ptr())   # noqa: E731
+    for name, fn, nbytes in (
+            ("hist_tiles", lambda: lib.ocv_hist_grid_u8(h, P(img), n, n, n, P(hist), _cabi.RAISR_DEVICE, ms), n * n + n // 32 * nx * 1024),
+            ("lut_apply", lambda: lib.ocv_histeq_global_u8(h, P(img), n, n, n, P(dst), n, P(lut), _cabi.RAISR_DEVICE, ms), 2 * n * n),
+            ("lut_blend", lambda: lib.ocv_histeq_local_block_u8(h, P(img), n, n, n, P(dst), n, P(maps), nx, ny, 256, 256, _cabi.RAISR_DEVICE, ms), 2 * n * n)):
+        t = timed(fn)
+        out[name] = dict(ms=round(t, 4), achieved_gbs=round(nbytes / t / 1e6, 1), frac=round(nbytes / t / 1e6 / peak, 3))
+    out["note"] = ("algorithmic bytes (source + destination once) / median kernel time of 10, device-resident; resize: 16 frames 1080p->4K; "
+                   "histeq: one 16384x16384 image; frac = of the measured HBM copy bandwidth %.0f GB/s" % peak)
+    return out
 
 
 def main():
@@ -222,19 +380,23 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=FRAMES, help="frames per GPU per step")
+    ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS), help="BASELINE.json config number: 3 = 4K->8K (default), 2 = 1080p->4K, 5 = 720p")
+    ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step (default: per config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the variants / band / next_rows sub-records")
     ap.add_argument("--filter-impl", type=int, default=None, help="1 octet (default), 0 block")
     ap.add_argument("--overlap", type=int, default=None, help="1: overlapped prep/filter pipeline, 0: serial")
-    ap.add_argument("--taps", default="fp32", choices=["fp32", "fp16"],
-                    help="fp16: taps rounded to half precision like the reference's (half)pf[...] (NOT the headline configuration)")
-    ap.add_argument("--chunk-mb", type=int, default=208, help="scratch budget per kernel launch in MiB (library default 208)")
+    ap.add_argument("--taps", default="auto", choices=["auto", "fp32", "fp16", "b24"],
+                    help="tap records in shared memory (auto = 24-bit when provably within 5e-5 of fp32 taps; fp16 is NOT a headline configuration)")
+    ap.add_argument("--chunk-mb", type=int, default=None, help="scratch budget per kernel launch in MiB (library default 208)")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    SW, SH = cfg["sw"], cfg["sh"]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        return run_reference(args, rank, world)
+        return run_reference(args, cfg, rank, world)
 
     import torch
     import torch.distributed as dist
@@ -247,7 +409,6 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from oclcomputervision_b200 import ClRaisr, synth, _cabi
-    import ctypes
     F = synth.random_filters(SCALE)
     r = ClRaisr(1, filters=F, device=local_rank, taps=args.taps)
     if args.filter_impl is not None:
@@ -257,9 +418,9 @@ def main():
     if args.chunk_mb is not None:
         r.set_option("chunk_budget_bytes", args.chunk_mb << 20)
     info = r.device_info()
-    n = args.frames
+    n = args.frames or cfg["frames"]
     dw, dh = SW * SCALE, SH * SCALE
-    host_src = make_inputs(n, rank)
+    host_src = make_inputs(cfg, n, rank)
     src = torch.from_numpy(host_src).cuda()
     dst = torch.empty((n, dh, dw), dtype=torch.uint8, device="cuda")
     stream = torch.cuda.current_stream()
@@ -274,29 +435,34 @@ def main():
     def step(timed):
         return r.upsample_device(src.data_ptr(), SW, SH, SW, dst.data_ptr(), dw, SCALE, n, np.uint8, timed=timed)
 
+    def timed_steps(k):
+        """k steps with per-kernel CUDA events inside; returns (elapsed ms, prep ms, filter ms) of this rank."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pm = fm = 0.0
+        barrier()
+        e0.record(stream)
+        for _ in range(k):
+            step(True)                       # per-kernel CUDA events on the launch stream, inside the region
+            a, b = r.last_kernel_ms()
+            pm += a; fm += b
+        e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1), pm, fm
+
     for _ in range(max(args.warmup, 3)):
         step(False)
     barrier()
     launches0 = r.launch_count()
     sampler = ClockSampler(local_rank, uuid=getattr(torch.cuda.get_device_properties(local_rank), "uuid", None))
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    prep_ms = filt_ms = 0.0
-    barrier()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step(True)                       # per-kernel CUDA events on the launch stream, inside the region
-        a, b = r.last_kernel_ms()
-        prep_ms += a; filt_ms += b
-    ev1.record(stream)
-    barrier()
+    elapsed_ms, prep_ms, filt_ms = timed_steps(args.steps)
     clocks = sampler.stop()
     launches = r.launch_count() - launches0
-    elapsed_ms = ev0.elapsed_time(ev1)
     t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
     value = world * px_per_step * args.steps / (elapsed_ms * 1e-3) / 1e6
+    Feff, tap_format, b24_bound = r.effective_filters(SCALE)
 
     # ---- end to end through the C-ABI with pinned host buffers (H2D + kernels + D2H per step)
     lib = _cabi.load()
@@ -318,10 +484,13 @@ def main():
         e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    ceil_s = copy_ceiling(torch, n * SW * SH, n * dw * dh, barrier)
+    te = torch.tensor([e2e_s, ceil_s], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * px_per_step * e2e_steps / float(te.item()) / 1e6
+    e2e_s, ceil_s = [float(x) for x in te.tolist()]
+    e2e_value = world * px_per_step * e2e_steps / e2e_s / 1e6
+    ceil_value = world * px_per_step / ceil_s / 1e6
     out_host = np.ctypeslib.as_array((ctypes.c_ubyte * (dw * dh)).from_address(hp_dst.value)).reshape(dh, dw)
     same_as_device = bool(np.array_equal(out_host, dst[0].cpu().numpy()))
     e2e_ms3 = [float(x) for x in ms3]
@@ -331,6 +500,44 @@ def main():
         _cabi.check(lib.raisr_upsample_u8(r._h, hp_src.value, SW, SH, SW, hp_dst.value, dw, dh, dw, SCALE, 1, _cabi.RAISR_HOST, one3))
     one_ms3 = [float(x) for x in one3]
     lib.raisr_host_free(hp_src); lib.raisr_host_free(hp_dst)
+
+    # ---- the same step with the other tap records (device-resident), and what each does to the output
+    variants = None
+    if not args.no_extras:
+        variants = {}
+        probe = synth.synthetic_frame(1080, 1920, 1000)
+        r.set_option("taps", 0)
+        base_out = r.upsample_f32(probe, SCALE)
+        r.set_stream(stream.cuda_stream)
+        for name, mode in (("fp32", 0), ("b24", 2), ("fp16", 1)):
+            r.set_option("taps", mode)
+            for _ in range(2):
+                step(False)
+            k = max(1, min(args.steps, 5))
+            el, pm, fm = timed_steps(k)
+            tv = torch.tensor([el], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+            el = float(tv.item())
+            r.set_stream(0)
+            dev = float(np.abs(r.upsample_f32(probe, SCALE) - base_out).max())
+            r.set_stream(stream.cuda_stream)
+            variants[name] = dict(value=round(world * px_per_step * k / (el * 1e-3) / 1e6, 1), unit="Mpix/s",
+                                  prep_ms_per_step=round(pm / k, 3), filter_ms_per_step=round(fm / k, 3),
+                                  max_abs_dev_vs_fp32_taps=dev,
+                                  roofline_frac=round(FLOP_PER_PX * px_per_step * k / ((pm + fm) * 1e-3) / 1e12 / (2.0 * 128 * info["sm_count"] * info["sm_clock_khz"] * 1e3 / 1e12), 4))
+        variants["note"] = ("fp32 = reference-precision taps; b24 = sign+exponent+15 mantissa bits (what 'auto' selects when the output provably stays "
+                            "within 5e-5 of fp32 taps); fp16 = the reference's own (half)pf[...] rounding (raisr.cl:328), outside the 1e-4 bar against fp32 taps, "
+                            "never the headline.  Deviation measured on one 1080p->4K frame, float output.")
+        r.set_option("taps", {"fp32": 0, "fp16": 1, "b24": 2, "auto": 3}[args.taps])
+        r.set_stream(0)
+
+    band = None
+    if not args.no_extras:
+        try:
+            band = band_record(torch, dist, r, rank, world, local_rank)
+        except Exception as e:       # the headline must survive a failure of the side record, which then says so
+            band = dict(error="%s: %s" % (type(e).__name__, e))
 
     if rank == 0:
         peaks = {}
@@ -346,40 +553,60 @@ def main():
         clk_hz = info["sm_clock_khz"] * 1e3
         filt_s = filt_ms * 1e-3
         px_total = px_per_step * args.steps
-        chunk_frames = max(1, min(n, int((args.chunk_mb << 20) // (((dh + 18 + 3) // 4 * 4) * (dw + 10) * 4))))   # frames per kernel launch (as in raisr_api.cu)
+        chunk_mb = args.chunk_mb or 208
+        chunk_frames = max(1, min(n, int((chunk_mb << 20) // (((dh + 18 + 3) // 4 * 4) * (dw + 10) * 4))))   # frames per kernel launch (as in raisr_api.cu)
+        launches_per_step = 2 * ((n + chunk_frames - 1) // chunk_frames)
+        prof = ncu_metrics("filter_octet_kernel", tap_format)
+        dom = dict(name="filter_octet_kernel<%s taps>" % tap_format, flop_per_px=FLOP_PER_PX_FILTER,
+                   achieved_tflops=round(FLOP_PER_PX_FILTER * px_total / filt_s / 1e12, 3),
+                   avg_launch_ms=round(filt_ms / (args.steps * launches_per_step / 2), 4),
+                   binding_resource="shared-memory data pipe, 1 wavefront (128 B) per clock per SM: each pixel needs its own 121 taps")
+        traffic = None
+        if prof:
+            frac = prof["smem_wavefronts_per_px"] * px_total / (filt_s * info["sm_count"] * clk_hz)
+            dom.update(smem_wavefronts_per_px=prof["smem_wavefronts_per_px"], smem_pipe_frac=round(min(frac, 1.0), 4),
+                       ncu_source=prof.get("source"))
+            if frac > 1.0:
+                dom["smem_pipe_frac_note"] = "profile figure and live time disagree (computed %.3f): re-capture the profile" % frac
+            traffic = int(prof["dram_bytes_per_px"] * chunk_frames * dw * dh)
         roofline = dict(bound="fp32_ffma", achieved=round(achieved_tf, 3), peak=round(peak_nominal, 2), unit="TFLOP/s",
-                        frac=round(achieved_tf / peak_nominal, 4),
-                        traffic=int(NCU_FILTER_DRAM_BYTES_PER_PX * chunk_frames * dw * dh),
-                        traffic_note="DRAM bytes per launch of the dominant kernel (ncu, profiles/); algorithmic %.0f" % (BYTES_PER_PX * chunk_frames * dw * dh),
+                        frac=round(achieved_tf / peak_nominal, 4), traffic=traffic,
+                        traffic_note=("DRAM read+write bytes per launch of the dominant kernel from the ncu capture named in dominant_kernel.ncu_source; "
+                                      if traffic else "no ncu capture of this kernel variant committed; ") + "algorithmic %.0f" % (BYTES_PER_PX * chunk_frames * dw * dh),
                         peak_source="2*128*SMs*clocks.max.sm (SURVEY 8(d)); measured register-only FFMA kernel: %.1f TFLOP/s" % ffma_meas,
                         frac_of_measured_ffma=round(achieved_tf / ffma_meas, 4),
                         flop_per_px=FLOP_PER_PX,
                         kernels=dict(prep_ms_per_step=round(prep_ms / args.steps, 3), filter_ms_per_step=round(filt_ms / args.steps, 3),
-                                     filter_share=round(filt_ms / (prep_ms + filt_ms), 3)),
-                        dominant_kernel=dict(
-                            name="filter_octet_kernel", flop_per_px=FLOP_PER_PX_FILTER,
-                            achieved_tflops=round(FLOP_PER_PX_FILTER * px_total / filt_s / 1e12, 3),
-                            binding_resource="shared-memory data pipe, 1 wavefront (128 B) per clock per SM: each pixel needs its own 484 B of fp32 taps",
-                            wavefronts_per_px=NCU_FILTER_WAVEFRONTS_PER_PX,
-                            smem_pipe_frac=round(NCU_FILTER_WAVEFRONTS_PER_PX * px_total / (filt_s * info["sm_count"] * clk_hz), 4)),
+                                     filter_share=round(filt_ms / (prep_ms + filt_ms), 3), launches_per_step=launches_per_step,
+                                     timing="CUDA events around every launch on the launch stream, inside the timed region"),
+                        dominant_kernel=dom,
                         hbm=dict(algorithmic_bytes_per_px=BYTES_PER_PX,
                                  achieved_gbs=round(BYTES_PER_PX * px_per_step * args.steps / kern_s / 1e9, 1),
                                  peak_gbs=hbm_peak, peak_source="MEASURED_PEAKS.json" if peaks else "fallback 6650"))
-        cb = None if (args.no_cpu_baseline or world > 1) else cpu_baseline()
+        cb = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(cfg)
+        next_rows = None
+        if not args.no_extras and world == 1:
+            try:
+                next_rows = next_rows_record(torch, lib, r._h, hbm_peak)
+            except Exception as e:
+                next_rows = dict(error="%s: %s" % (type(e).__name__, e))
         line = dict(metric="RAISR 2x output Mpix/s", value=round(value, 1), unit="Mpix/s", n_gpus=world, steps=args.steps,
                     warmup=max(args.warmup, 3), ms_per_step=round(elapsed_ms / args.steps, 3), higher_is_better=True,
                     scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                    config=dict(workload="RAISR 2x 1080p->4K luma u8->u8, batch of %d synthetic frames per GPU, "
-                                         "random-init 24x3x3x4x121 fp32 table (BASELINE configs[1])%s" % (n, "" if args.taps == "fp32" else "; NON-DEFAULT: taps rounded to fp16 (raisr.cl:328), fp32 arithmetic"),
+                    config=dict(workload=workload_text(cfg, n, "" if args.taps != "fp16" else "; NON-DEFAULT: taps rounded to fp16 (raisr.cl:328), fp32 arithmetic"),
                                 frames_per_gpu=n, src="%dx%d" % (SW, SH), dst="%dx%d" % (dw, dh), parallelism="frames sharded, no collective",
+                                taps="%s (requested %s; b24 output bound %.2e vs fp32 taps; arithmetic fp32)" % (tap_format, args.taps, b24_bound),
                                 l2="per-step working set (%.0f MB in + %.0f MB out) exceeds the 126 MB L2" % (n * SW * SH / 1e6, n * dw * dh / 1e6),
                                 device=info["name"]),
                     clocks=clocks, gpu_launches=int(launches),
                     e2e=dict(value=round(e2e_value, 1), unit="Mpix/s", h2d_bytes_per_step=n * SW * SH, d2h_bytes_per_step=n * dw * dh,
                              h2d_kernel_d2h_ms=[round(x, 3) for x in e2e_ms3], one_frame_h2d_kernel_d2h_ms=[round(x, 3) for x in one_ms3],
                              matches_device_path=same_as_device,
+                             copy_ceiling=dict(value=round(ceil_value, 1), unit="Mpix/s", gbs=round(world * (n * SW * SH + n * dw * dh) / ceil_s / 1e9, 1),
+                                               note="the step's H2D and D2H bytes moved by bare cudaMemcpyAsync (pinned, two streams), all ranks at once, no kernels"),
+                             frac_of_copy_ceiling=round(e2e_value / ceil_value, 3),
                              api="raisr_upsample_u8(where=RAISR_HOST), pinned buffers", host_affinity=numa),
-                    roofline=roofline, cpu_baseline=cb)
+                    roofline=roofline, cpu_baseline=cb, variants=variants, band=band, next_rows=next_rows)
         print(json.dumps(line), flush=True)
     r.close()
     if world > 1:

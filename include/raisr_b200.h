@@ -59,7 +59,8 @@ int raisr_set_filters(raisr_t* h, int scale, const float* table, size_t n_floats
  * oracle).  table_out (may be NULL) receives the effective taps in the layout of raisr_set_filters: the table as
  * given for tap format 0 (fp32), every tap rounded to fp16 for format 1, and the 24-bit values for format 2 (sign,
  * exponent and 15 mantissa bits stored, see csrc/raisr_octet.cuh).  tap_format / b24_bound (may be NULL): the format
- * in use for this scale, and max over filters of sum_k |tap_b24 - tap| -- a bound on |output - fp32-tap output|. */
+ * in use for this scale, and the bound on |output - fp32-tap output| of the 24-bit records: max over filters of
+ * max(sum of the positive, sum of the negative tap errors) -- the patch values lie in [0,1]. */
 int raisr_get_effective_filters(raisr_t* h, int scale, float* table_out, size_t n_floats, int* tap_format,
                                 float* b24_bound);
 
@@ -95,8 +96,9 @@ int raisr_set_stream(raisr_t* h, void* cuda_stream);
  *   "taps"      precision of the taps in the resident shared-memory table; arithmetic is fp32 in every mode.
  *               0 = fp32.  1 = fp16, as the reference's `(half)pf[...]` (raisr.cl:328) does.  2 = b24: sign, exponent
  *               and 15 mantissa bits (three quarters of the tap stream that bounds the filter kernel).  3 = auto
- *               (default): b24 when sum_k |tap_b24 - tap| <= 5e-5 for every filter of the table, i.e. when the
- *               output provably stays within half the 1e-4 parity tolerance of the fp32-tap result, else fp32.
+ *               (default): b24 when, for every filter of the table, the positive and the negative tap errors each sum
+ *               to <= 5e-5, i.e. when the output provably stays within half the 1e-4 parity tolerance of the
+ *               fp32-tap result (patch values lie in [0,1]), else fp32.
  *               Gray path only; the colour path keeps fp32 (or fp16) taps.  Re-packs the tables already set.
  *   "taps_fp16" older spelling: 1 = "taps" 1, 0 = "taps" 3. */
 int raisr_set_option(raisr_t* h, const char* key, long long value);
@@ -204,6 +206,26 @@ int raisr_ipc_open(const unsigned char handle_in[64], void** dev_ptr_out);
 int raisr_ipc_close(void* dev_ptr);
 int raisr_p2p_copy2d(raisr_t* h, void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
                      size_t width_bytes, size_t rows);
+
+/* Stream-ordered hand-shake between the GPUs of a row-band job, no host synchronisation and no collective: a
+ * 32-bit sequence word in device memory (normally inside an allocation the peers have mapped with raisr_ipc_open).
+ * raisr_flag_set enqueues "publish `value`" after everything already enqueued on the handle's stream (with a
+ * system-scope fence, so rows copied before it are visible to peers that see the value); raisr_flag_wait enqueues
+ * "do not start later work of this stream before *flag has reached `value`" (wrap-safe comparison).  A wait that
+ * is not satisfied within timeout_ms gives up; the next raisr_sync() then returns RAISR_E_STATE. */
+int raisr_flag_set(raisr_t* h, void* dev_flag, unsigned value);
+int raisr_flag_wait(raisr_t* h, const void* dev_flag, unsigned value, int timeout_ms);
+
+/* 2-D copy on the handle's stream: direction 0 = host to device, 1 = device to host, 2 = device to device (also
+ * from peer memory, like raisr_p2p_copy2d).  Asynchronous; host memory should be pinned. */
+int raisr_copy2d(raisr_t* h, void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
+                 size_t rows, int direction);
+
+/* CUDA-event stopwatch on the handle's stream (the reference times its queue with OpenCL profiling events,
+ * raisr.py:12-16): raisr_timer_mark records slot 0..7; raisr_timer_elapsed_ms waits for slot_to and returns the
+ * device time between the two marks. */
+int raisr_timer_mark(raisr_t* h, int slot);
+int raisr_timer_elapsed_ms(raisr_t* h, int slot_from, int slot_to, float* ms);
 
 /* Plain device allocations on the handle's device (cudaMalloc, so they can be exported with
  * raisr_ipc_export; framework caching allocators hand out sub-blocks that cannot). */

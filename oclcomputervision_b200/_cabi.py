@@ -53,6 +53,11 @@ SIGNATURES = {
     "raisr_ipc_open": (c_int, [POINTER(c_ubyte), POINTER(c_void_p)]),
     "raisr_ipc_close": (c_int, [c_void_p]),
     "raisr_p2p_copy2d": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t]),
+    "raisr_flag_set": (c_int, [c_void_p, c_void_p, ctypes.c_uint]),
+    "raisr_flag_wait": (c_int, [c_void_p, c_void_p, ctypes.c_uint, c_int]),
+    "raisr_copy2d": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t, c_int]),
+    "raisr_timer_mark": (c_int, [c_void_p, c_int]),
+    "raisr_timer_elapsed_ms": (c_int, [c_void_p, c_int, c_int, POINTER(c_float)]),
     "raisr_dev_alloc": (c_int, [c_void_p, POINTER(c_void_p), c_size_t]),
     "raisr_dev_free": (c_int, [c_void_p, c_void_p]),
     "raisr_host_alloc": (c_int, [POINTER(c_void_p), c_size_t]),

@@ -320,6 +320,25 @@ int upsample_impl(raisr_ctx* h, const uint8_t* src, int sw, int sh, size_t src_p
     return 0;
 }
 
+// Cross-GPU ordering of the row-band path without host synchronisation: a 32-bit sequence word in (peer-mapped)
+// device memory, written by the producer's stream and polled by the consumer's stream.
+__global__ void flag_set_kernel(volatile unsigned* flag, unsigned value)
+{
+    __threadfence_system();          // everything this stream wrote before (the band's source rows) is visible first
+    *flag = value;
+    __threadfence_system();
+}
+
+__global__ void flag_wait_kernel(const volatile unsigned* flag, unsigned value, long long timeout_cycles, int* timed_out)
+{
+    const long long t0 = clock64();
+    while ((int)(*flag - value) < 0) {           // sequence numbers wrap
+        if (clock64() - t0 > timeout_cycles) { *timed_out = 1; return; }
+        __nanosleep(256);
+    }
+    __threadfence_system();
+}
+
 __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters)
 {
     float a[16];
@@ -407,6 +426,8 @@ void raisr_destroy(raisr_t* h)
     for (int b = 0; b < 2; ++b) { h->dsrc[b].release(); h->ddst[b].release(); }
     for (auto e : h->ev_pool) cudaEventDestroy(e);
     if (h->scratch_ev) cudaEventDestroy(h->scratch_ev);
+    if (h->flag_err) cudaFree(h->flag_err);
+    for (auto e : h->timer_ev) if (e) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
@@ -439,8 +460,9 @@ static int upload_table(raisr_ctx* h, int scale)
         }
     if (int rc = t.block.ensure(blk.size() * sizeof(float))) return rc;
     if (int rc = t.octet.ensure(oct.size() * sizeof(float))) return rc;
-    // 24-bit records and the bound on what they can change: |out_b24 - out_fp32| <= sum_k |tap_b24 - tap_fp32| * |patch_k|
-    // and the patch is an upscaled image in [0,1] (bilinear; the bicubic variant clamps).  "auto" uses them only while
+    // 24-bit records and the bound on what they can change: out_b24 - out_fp32 = sum_k (tap_b24 - tap_fp32) * patch_k and
+    // the patch is an upscaled image in [0,1] (bilinear; the bicubic variant clamps), so the difference lies between
+    // minus the sum of the negative tap errors and the sum of the positive ones.  "auto" uses the records only while
     // that bound stays under half of the 1e-4 parity tolerance.
     std::vector<uint8_t> rec24;
     std::vector<float> eff24;
@@ -454,12 +476,16 @@ static int upload_table(raisr_ctx* h, int scale)
             for (int b = 0; b < nb; ++b) {
                 const size_t o = ((size_t)b * ss + type) * kTaps;
                 octet_pack_filter_b24(t.host.data() + o, &rec24[((size_t)type * nb + b) * kOctBytesB24], scale, &eff24[o]);
-                double sum = 0;
-                for (int k = 0; k < kTaps; ++k) sum += fabs((double)eff24[o + k] - (double)t.host[o + k]);
-                worst = std::max(worst, sum);
+                double up = 0, down = 0;   // the patch values lie in [0,1]: the worst case takes the errors of one sign only
+                for (int k = 0; k < kTaps; ++k) {
+                    const double d = (double)eff24[o + k] - (double)t.host[o + k];
+                    if (d > 0) up += d; else down -= d;
+                }
+                worst = std::max(worst, std::max(up, down));
             }
         t.b24_bound = (float)worst;
         if (h->taps_mode == 2 || worst <= 5.0e-5) t.format = kTapsB24;
+        if (h->overlap) t.format = kTapsF32;   // the single-buffered kernel of the experimental overlapped pipeline holds fp32 records
     }
     if (t.format == kTapsB24) t.eff = eff24;
     else t.eff.assign(table, table + t.host.size());
@@ -538,7 +564,16 @@ int raisr_set_option(raisr_t* h, const char* key, long long value)
 {
     if (!h || !key) return fail(RAISR_E_ARG, "null argument");
     if (!strcmp(key, "filter_impl")) { h->filter_impl = value ? 1 : 0; return 0; }
-    if (!strcmp(key, "overlap")) { h->overlap = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "overlap")) {
+        const int v = value ? 1 : 0;
+        if (v != h->overlap) {
+            h->overlap = v;
+            for (int sc = 2; sc <= 4; ++sc)
+                if (h->tables[sc].set)
+                    if (int rc = upload_table(h, sc)) return rc;
+        }
+        return 0;
+    }
     if (!strcmp(key, "prep_impl")) { h->prep_impl = value == 1 ? 1 : 2; return 0; }
     if (!strcmp(key, "filter_pipe")) { h->filter_pipe = value ? 1 : 0; return 0; }
     if (!strcmp(key, "color_filter_impl")) { h->color_filter_impl = value == 1 ? 1 : 2; return 0; }
@@ -1126,6 +1161,62 @@ int raisr_p2p_copy2d(raisr_t* h, void* dst, size_t dst_pitch, const void* src, s
     return 0;
 }
 
+int raisr_copy2d(raisr_t* h, void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows,
+                 int direction)
+{
+    if (!h || !dst || !src) return fail(RAISR_E_ARG, "null argument");
+    if (direction < 0 || direction > 2) return fail(RAISR_E_ARG, "direction must be 0 (host to device), 1 (device to host) or 2 (device to device)");
+    if (dst_pitch < width_bytes || src_pitch < width_bytes) return fail(RAISR_E_ARG, "pitch smaller than a row");
+    Guard guard(h->device);
+    const cudaMemcpyKind kind = direction == 0 ? cudaMemcpyHostToDevice : direction == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    CUDA_TRY(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, kind, h->stream()));
+    return 0;
+}
+
+int raisr_timer_mark(raisr_t* h, int slot)
+{
+    if (!h || slot < 0 || slot >= 8) return fail(RAISR_E_ARG, "timer slot must be 0..7");
+    Guard guard(h->device);
+    if (!h->timer_ev[slot]) CUDA_TRY(cudaEventCreate(&h->timer_ev[slot]));
+    CUDA_TRY(cudaEventRecord(h->timer_ev[slot], h->stream()));
+    return 0;
+}
+
+int raisr_timer_elapsed_ms(raisr_t* h, int slot_from, int slot_to, float* ms)
+{
+    if (!h || !ms || slot_from < 0 || slot_from >= 8 || slot_to < 0 || slot_to >= 8) return fail(RAISR_E_ARG, "bad timer slots");
+    Guard guard(h->device);
+    if (!h->timer_ev[slot_from] || !h->timer_ev[slot_to]) return fail(RAISR_E_STATE, "timer slot was never marked");
+    CUDA_TRY(cudaEventSynchronize(h->timer_ev[slot_to]));
+    CUDA_TRY(cudaEventElapsedTime(ms, h->timer_ev[slot_from], h->timer_ev[slot_to]));
+    return 0;
+}
+
+int raisr_flag_set(raisr_t* h, void* dev_flag, unsigned value)
+{
+    if (!h || !dev_flag) return fail(RAISR_E_ARG, "null argument");
+    Guard guard(h->device);
+    flag_set_kernel<<<1, 1, 0, h->stream()>>>((volatile unsigned*)dev_flag, value);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int raisr_flag_wait(raisr_t* h, const void* dev_flag, unsigned value, int timeout_ms)
+{
+    if (!h || !dev_flag) return fail(RAISR_E_ARG, "null argument");
+    Guard guard(h->device);
+    if (!h->flag_err) {
+        CUDA_TRY(cudaMalloc(&h->flag_err, sizeof(int)));
+        CUDA_TRY(cudaMemset(h->flag_err, 0, sizeof(int)));
+    }
+    const long long cycles = (long long)std::max(timeout_ms, 1) * (long long)std::max(h->clock_khz, 1000);   // kHz = cycles per ms
+    flag_wait_kernel<<<1, 1, 0, h->stream()>>>((const volatile unsigned*)dev_flag, value, cycles, h->flag_err);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 int raisr_dev_alloc(raisr_t* h, void** p, size_t bytes)
 {
     if (!h || !p) return fail(RAISR_E_ARG, "null argument");
@@ -1179,6 +1270,14 @@ int raisr_sync(raisr_t* h)
     CUDA_TRY(cudaStreamSynchronize(h->own_stream));
     CUDA_TRY(cudaStreamSynchronize(h->h2d_stream));
     CUDA_TRY(cudaStreamSynchronize(h->d2h_stream));
+    if (h->flag_err) {
+        int bad = 0;
+        CUDA_TRY(cudaMemcpy(&bad, h->flag_err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (bad) {
+            CUDA_TRY(cudaMemset(h->flag_err, 0, sizeof(int)));
+            return fail(RAISR_E_STATE, "raisr_flag_wait timed out: a peer never published the expected sequence number");
+        }
+    }
     return 0;
 }
 

@@ -54,7 +54,7 @@ struct ScaleTable {
     std::vector<float> host;  // the caller's table as given (repacked when the tap precision option changes)
     std::vector<float> eff;   // the tap values the active gray kernel multiplies by, reference layout
     int format = raisr::kTapsF32;    // tap format the gray octet kernel uses for this scale
-    float b24_bound = 0;      // max over filters of sum_k |b24 tap - fp32 tap|: bound on |out_b24 - out_fp32| for patches in [0,1]
+    float b24_bound = 0;      // max over filters of max(sum of positive, sum of negative tap errors): bounds |out_b24 - out_fp32| for patches in [0,1]
     bool set = false;
 };
 
@@ -93,6 +93,8 @@ struct raisr_ctx {
         scratch_stream = st;
         scratch_busy = true;
     }
+    cudaEvent_t timer_ev[8] = {};  // raisr_timer_mark slots
+    int* flag_err = nullptr;      // device word set by a raisr_flag_wait that timed out (reported by raisr_sync)
     long long launches = 0;
     float last_prep_ms = 0, last_filter_ms = 0;
     int filter_impl = 1;  // 0 = block (v1), 1 = octet

@@ -138,7 +138,7 @@ def test_tap_formats_fp32_b24_auto(s):
     a table whose bound is larger; "b24" and "fp32" force either.  Outputs of b24 stay within the reported bound of
     the fp32-tap output, and the oracle run on the effective taps reproduces them to 5e-6."""
     src = synth.synthetic_frame(150, 210, seed=44)
-    F = synth.random_filters(s, seed=9)
+    F = synth.random_filters(s)        # the bench table of this scale: its b24 bound is 4.4e-5 / 4.5e-5
     outs = {}
     for taps in ("fp32", "b24", "auto"):
         r = ClRaisr(1, device=0, taps=taps)
@@ -207,8 +207,8 @@ def test_reference_demo_flow_both_modes(tmp_path, img_gray):
     print("demo imgGray=%d: elapsed %.3f + %.3f + %.3f ms, PSNR cubic %.3f raisr %.3f" %
           ((img_gray,) + tuple(res["elapsed"]) + (res["psnr_cubic"], res["psnr_raisr"])))
     assert res["out"].shape[:2] == (192, 256) and res["out"].shape[2] == (3 if img_gray else 4)
-    # identity-plus-noise filters keep the result near the bilinear one
-    assert res["psnr_raisr"] > res["psnr_cubic"] - 6.0 and res["psnr_cubic"] > 20.0
+    # identity-plus-noise filters (random-init, sigma 0.02 on 121 taps) keep the result in the neighbourhood of the bilinear one
+    assert res["psnr_raisr"] > 30.0 and res["psnr_cubic"] > 30.0
     # the demo's RAISR image is what the class computes: re-run the core call and compare
     bgr = cv2.resize(hr, (128, 96))
     r = ClRaisr(img_gray, filters=F)
