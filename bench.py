@@ -5,7 +5,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the hot path over one batch of synthetic luma frames (u8 in, u8 out).  The default workload
-is the size north_star quotes its target on, BASELINE.json configs[2]: 4K -> 8K, 16 frames per GPU per step
+is the size north_star quotes its target on, BASELINE.json configs[2]: 4K -> 8K, 32 frames per GPU per step
 (`--config 2` = configs[1], 1080p -> 4K x 64 frames; `--config 5` = configs[4], 720p x 256 frames).  With N GPUs every
 rank processes its own frames (frames are independent, no collective: weak scaling); `value` is the whole-job
 output Mpix/s.
@@ -44,7 +44,7 @@ sys.path.insert(0, ROOT)
 SCALE = 2
 CONFIGS = {   # BASELINE.json config number (1-based) -> source size, frames per GPU per step
     2: dict(sw=1920, sh=1080, frames=64, name="1080p->4K", baseline="configs[1]"),
-    3: dict(sw=3840, sh=2160, frames=16, name="4K->8K", baseline="configs[2] (north_star target size; 16 of its 512 frames per GPU per step)"),
+    3: dict(sw=3840, sh=2160, frames=32, name="4K->8K", baseline="configs[2] (north_star target size; 32 of its 512 frames per GPU per step)"),
     5: dict(sw=1280, sh=720, frames=256, name="720p->1440p", baseline="configs[4] (256 of its 2048 frames per GPU per step)"),
 }
 FLOP_PER_PX = 412.0                             # SURVEY.md 8(d), minimal form: whole path
@@ -605,6 +605,9 @@ def main():
                              copy_ceiling=dict(value=round(ceil_value, 1), unit="Mpix/s", gbs=round(world * (n * SW * SH + n * dw * dh) / ceil_s / 1e9, 1),
                                                note="the step's H2D and D2H bytes moved by bare cudaMemcpyAsync (pinned, two streams), all ranks at once, no kernels"),
                              frac_of_copy_ceiling=round(e2e_value / ceil_value, 3),
+                             bound=dict(value=round(min(ceil_value, value), 1), unit="Mpix/s",
+                                        by="kernels (device-resident value)" if value <= ceil_value else "host copies (copy_ceiling)"),
+                             frac_of_bound=round(e2e_value / min(ceil_value, value), 3),
                              api="raisr_upsample_u8(where=RAISR_HOST), pinned buffers", host_affinity=numa),
                     roofline=roofline, cpu_baseline=cb, variants=variants, band=band, next_rows=next_rows)
         print(json.dumps(line), flush=True)

@@ -160,7 +160,7 @@ int enqueue_frames(raisr_ctx* h, const uint8_t* dsrc, int sw, int sh, size_t src
     size_t per_frame = g.uext_frame * sizeof(float);
     int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nf, h->chunk_budget / std::max<size_t>(per_frame, 1)));
     if (int rc = h->uext.ensure(per_frame * chunk)) return rc;
-    if (int rc = h->hash.ensure(g.hash_frame * chunk)) return rc;
+    if (int rc = h->hash.ensure_zero(g.hash_frame * chunk)) return rc;
     const int nchunks = (nf + chunk - 1) / chunk;
     PrepParams pp;
     FilterParams fp;
@@ -171,7 +171,7 @@ int enqueue_frames(raisr_ctx* h, const uint8_t* dsrc, int sw, int sh, size_t src
         // of chunk c.  Two scratch sets, two internal streams, the filter stream has priority so that
         // its CTAs are placed first when both kernels become runnable together.
         if (int rc = h->uext2.ensure(per_frame * chunk)) return rc;
-        if (int rc = h->hash2.ensure(g.hash_frame * chunk)) return rc;
+        if (int rc = h->hash2.ensure_zero(g.hash_frame * chunk)) return rc;
         cudaStream_t sp = h->prep_stream, sf = h->filt_stream;
         auto E = [&](int c, int k) { return h->ev(ev_base + 2 + (size_t)c * 4 + k); };   // 0/1 prep start/stop, 2/3 filter start/stop
         cudaEventRecord(h->ev(ev_base), st);
@@ -183,11 +183,11 @@ int enqueue_frames(raisr_ctx* h, const uint8_t* dsrc, int sw, int sh, size_t src
                         (uint8_t*)(b ? h->hash2.p : h->hash.p), pp, fp);
             if (c >= 2) cudaStreamWaitEvent(sp, E(c - 2, 3), 0);   // scratch set b is free again
             cudaEventRecord(E(c, 0), sp);
-            if (int rc = launch_prep(h, pp, scale, sp, false, c == 0 ? 0 : 1)) return rc;
+            if (int rc = launch_prep(h, pp, scale, sp, false, (c == 0 || h->overlap == 2) ? 0 : 1)) return rc;
             cudaEventRecord(E(c, 1), sp);
             cudaStreamWaitEvent(sf, E(c, 1), 0);
             cudaEventRecord(E(c, 2), sf);
-            if (int rc = launch_filter<OutT>(h, fp, scale, sf, true)) return rc;
+            if (int rc = launch_filter<OutT>(h, fp, scale, sf, h->overlap != 2)) return rc;
             cudaEventRecord(E(c, 3), sf);
         }
         cudaStreamWaitEvent(st, E(nchunks - 1, 3), 0);
@@ -485,7 +485,7 @@ static int upload_table(raisr_ctx* h, int scale)
             }
         t.b24_bound = (float)worst;
         if (h->taps_mode == 2 || worst <= 5.0e-5) t.format = kTapsB24;
-        if (h->overlap) t.format = kTapsF32;   // the single-buffered kernel of the experimental overlapped pipeline holds fp32 records
+        if (h->overlap == 1) t.format = kTapsF32;   // the single-buffered kernel of the experimental overlapped pipeline holds fp32 records
     }
     if (t.format == kTapsB24) t.eff = eff24;
     else t.eff.assign(table, table + t.host.size());
@@ -565,7 +565,7 @@ int raisr_set_option(raisr_t* h, const char* key, long long value)
     if (!h || !key) return fail(RAISR_E_ARG, "null argument");
     if (!strcmp(key, "filter_impl")) { h->filter_impl = value ? 1 : 0; return 0; }
     if (!strcmp(key, "overlap")) {
-        const int v = value ? 1 : 0;
+        const int v = value == 2 ? 2 : (value ? 1 : 0);   // 2: the normal kernels on two streams (each fills the other's tail)
         if (v != h->overlap) {
             h->overlap = v;
             for (int sc = 2; sc <= 4; ++sc)
@@ -723,7 +723,7 @@ static int upsample_bgra_impl(raisr_t* h, const uint8_t* src, int sw, int sh, si
     const size_t src_frame = src_pitch * sh, dst_frame = dst_pitch * dh;
     const size_t fpitch = round_up((size_t)dw, 4), fplane = fpitch * dh;
     if (int rc = h->uext.ensure(g.uext_frame * sizeof(float) * 4)) return rc;
-    if (int rc = h->hash.ensure(g.hash_frame)) return rc;
+    if (int rc = h->hash.ensure_zero(g.hash_frame)) return rc;
     if (int rc = h->cplanes.ensure(fplane * sizeof(float) * 4)) return rc;
     if (where == RAISR_DEVICE) {
         cudaStream_t st = h->stream();
@@ -982,7 +982,7 @@ int raisr_debug_hash(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_
     const int dw = sw * scale, dh = sh * scale;
     Geometry g = make_geometry(sw, dh, scale);
     if (int rc = h->uext.ensure(g.uext_frame * sizeof(float))) return rc;
-    if (int rc = h->hash.ensure(g.hash_frame)) return rc;
+    if (int rc = h->hash.ensure_zero(g.hash_frame)) return rc;
     const size_t plane = (size_t)dw * dh;
     const uint8_t* dsrc = src;
     void* outs[5] = {hash, angle, l1, coherence, upscaled};
@@ -1030,7 +1030,7 @@ int raisr_debug_hash_bgra(raisr_t* h, const uint8_t* src, int sw, int sh, size_t
     const int dw = sw * scale, dh = sh * scale;
     Geometry g = make_geometry(sw, dh, scale);
     if (int rc = h->uext.ensure(g.uext_frame * sizeof(float) * 4)) return rc;
-    if (int rc = h->hash.ensure(g.hash_frame)) return rc;
+    if (int rc = h->hash.ensure_zero(g.hash_frame)) return rc;
     const size_t plane = (size_t)dw * dh;
     const uint8_t* dsrc = src;
     void* outs[4] = {hash, angle, l1, coherence};
@@ -1101,7 +1101,7 @@ int raisr_upsample_band_u8(raisr_t* h, const uint8_t* src_rows_ptr, int sw, int 
     cudaStream_t st = h->stream();
     Geometry g = make_geometry(sw, dst_rows, scale);
     if (int rc = h->uext.ensure(g.uext_frame * sizeof(float))) return rc;
-    if (int rc = h->hash.ensure(g.hash_frame)) return rc;
+    if (int rc = h->hash.ensure_zero(g.hash_frame)) return rc;
     PrepParams pp{};
     pp.src = src_rows_ptr; pp.src_pitch = src_pitch; pp.src_frame_stride = 0;
     pp.sw = sw; pp.sh_glob = global_sh; pp.src_row0 = src_row0; pp.src_rows = src_rows;

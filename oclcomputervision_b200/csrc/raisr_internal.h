@@ -38,6 +38,14 @@ struct DevBuf {
         bytes = need;
         return 0;
     }
+    // as ensure(), and a (re)allocated buffer starts out all zero
+    int ensure_zero(size_t need)
+    {
+        if (need <= bytes) return 0;
+        if (int rc = ensure(need)) return rc;
+        if (cudaMemset(p, 0, bytes) != cudaSuccess) return fail(RAISR_E_CUDA, "cudaMemset(%zu) failed", bytes);
+        return 0;
+    }
     void release()
     {
         if (p) cudaFree(p);

@@ -191,12 +191,15 @@ struct OctetGeom {
 
 __host__ __device__ constexpr int octet_record_bytes(int tf) { return tf == kTapsF16 ? kOctStrideH * 2 : tf == kTapsB24 ? kOctBytesB24 : kOctStride * 4; }
 
+// The patch look-ahead of an item's last pixel reads up to S tile columns past the last tile buffer.
+constexpr int kOctetTailPad = 2048;
+
 template <int S, int NBUF = 2>
 inline size_t octet_smem_bytes(int n_buckets, int tf = kTapsF32)
 {
     using G = OctetGeom<S>;
     const size_t rec = octet_record_bytes(tf);
-    return (size_t)n_buckets * rec + NBUF * (size_t)G::BUF_BYTES + 32;   // + four mbarriers (full / empty per buffer)
+    return (size_t)n_buckets * rec + NBUF * (size_t)G::BUF_BYTES + 32 + kOctetTailPad;   // + mbarriers / counters + look-ahead slack
 }
 
 __device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gptr)
@@ -410,7 +413,6 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1)
     const float4* tab_lane = reinterpret_cast<const float4*>(tab) + lane8;
     const unsigned tab_lane_s = (unsigned)__cvta_generic_to_shared(tab_lane);
     const unsigned omask = 0xffu << (tid & 24);  // the eight lanes of this octet
-    const unsigned maxb = (unsigned)(p.n_buckets - 1);
 
     int it = 0;
     for (int tile = worker; tile < ntiles; tile += nworkers, ++it) {
@@ -453,8 +455,10 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1)
             }
 #pragma unroll
             for (int t = 0; t < G::NEWP; ++t) w5[5 - G::NEWP + t] = base[off_part[t]];
+            // hash bytes are always < n_buckets: the prep kernel writes valid buckets only and the host zero-fills the
+            // scratch when it allocates it (padding bytes never hold anything else), so no clamp is needed here
             uint2 hb = hrow[0];
-            unsigned bucket = min(hb.x & 0xffu, maxb);
+            unsigned bucket = hb.x & 0xffu;
             const float4* tp = tab_lane + bucket * (REC / 16);
             float4 t0 = {}, t1 = {}, t2 = {}, t3 = {};
             uint4 q0 = {}, q1 = {}, q2 = {};
@@ -474,8 +478,8 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1)
                 for (int b = 0; b < 8; ++b) {
                     // taps of the next pixel: each 16-byte chunk is reloaded as soon as the FMAs of this
                     // pixel have read it, and only if the next pixel hashes to another bucket
-                    unsigned nbucket = (b < 7) ? (((b + 1 < 4 ? hb.x : hb.y) >> (8 * ((b + 1) & 3))) & 0xffu) : (hnext.x & 0xffu);
-                    nbucket = min(nbucket, maxb);
+                    // byte (b+1)&3 of the hash word, zero-extended, in one PRMT
+                    const unsigned nbucket = (b < 7) ? __byte_perm(b + 1 < 4 ? hb.x : hb.y, 0u, 0x4440u | ((b + 1) & 3)) : (hnext.x & 0xffu);
                     const bool reload = nbucket != bucket;
                     bucket = nbucket;
                     const unsigned tpa = tab_lane_s + nbucket * REC;
@@ -530,8 +534,10 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1)
                     lds128_if(t3, tpa + 384, reload);
                     }
                     // fresh patch values of the next pixel overwrite the slots this pixel has just consumed
+                    // (for the last pixel of an item these loads run up to S columns past the tile: still inside the
+                    // padded shared-memory allocation, and the values are never used)
                     const int npix = b0 + b + 1;
-                    if (npix < C::IW) {
+                    {
                         const int on = S * (b + 1);
 #pragma unroll
                         for (int t = 0; t < G::NEWF; ++t) w11[(on + kFlen - G::NEWF + t) % G::WF] = pf[(S * npix + kFlen - G::NEWF + t) * G::PT];
