@@ -575,6 +575,7 @@ int raisr_set_option(raisr_t* h, const char* key, long long value)
         return 0;
     }
     if (!strcmp(key, "prep_impl")) { h->prep_impl = value == 1 ? 1 : 2; return 0; }
+    if (!strcmp(key, "resize_fast")) { h->resize_fast = value ? 1 : 0; return 0; }
     if (!strcmp(key, "filter_pipe")) { h->filter_pipe = value ? 1 : 0; return 0; }
     if (!strcmp(key, "color_filter_impl")) { h->color_filter_impl = value == 1 ? 1 : 2; return 0; }
     if (!strcmp(key, "quirks")) { h->as_written = value ? 1 : 0; return 0; }
@@ -631,8 +632,13 @@ int raisr_bilinear_u8(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src
     cudaEventRecord(h->ev(1), st);
     // stage 1 alone == the stand-alone bilinear_lds resizer (same map, same expression order; tests pin the two)
     ResizeParams rp{dsrc, src_pitch, src_frame, ddst, dst_pitch, dst_frame, sw, sh, dw, dh, 1, 0};
-    dim3 grid((dw + 255) / 256, (dh + kResizeRows - 1) / kResizeRows, n_frames);
-    resize_kernel<1><<<grid, 256, 0, st>>>(rp);
+    if (resize_fast_ok(rp) && h->resize_fast) {
+        dim3 grid((dw + kFastCols - 1) / kFastCols, (dh + kFastRows - 1) / kFastRows, n_frames);
+        resize_bilinear_gray_kernel<<<grid, kFastThreads, (size_t)resize_fast_win_floats(rp) * sizeof(float), st>>>(rp);
+    } else {
+        dim3 grid((dw + 255) / 256, (dh + kResizeRows - 1) / kResizeRows, n_frames);
+        resize_kernel<1><<<grid, 256, 0, st>>>(rp);
+    }
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     cudaEventRecord(h->ev(2), st);
@@ -825,7 +831,10 @@ int raisr_resize_u8(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_p
     ResizeParams rp{dsrc, src_pitch, src_frame, ddst, dst_pitch, dst_frame, sw, sh, dw, dh, channels, mode};
     dim3 grid((dw + 255) / 256, (dh + kResizeRows - 1) / kResizeRows, n_frames);
     if (channels == 4) resize_kernel<4><<<grid, 256, 0, st>>>(rp);
-    else resize_kernel<1><<<grid, 256, 0, st>>>(rp);
+    else if (resize_fast_ok(rp) && h->resize_fast) {
+        dim3 fgrid((dw + kFastCols - 1) / kFastCols, (dh + kFastRows - 1) / kFastRows, n_frames);
+        resize_bilinear_gray_kernel<<<fgrid, kFastThreads, (size_t)resize_fast_win_floats(rp) * sizeof(float), st>>>(rp);
+    } else resize_kernel<1><<<grid, 256, 0, st>>>(rp);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     cudaEventRecord(h->ev(2), st);

@@ -13,6 +13,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "packed_f32.cuh"
+
 namespace raisr {
 
 struct ResizeParams {
@@ -184,6 +186,149 @@ __global__ void __launch_bounds__(256) resize_kernel(const ResizeParams p)
     };
     if (staged) run(fetch_win);
     else run(fetch_gmem);
+}
+
+// ---- fast path of the two bilinear modes for 8-bit gray images (also what the SHIPPED raisr kernel computes,
+// raisr.cl:219-230): a byte stream of 1 + 1/s^2 bytes per output pixel that the generic kernel above ran at 9 % of
+// the HBM roofline (one byte store and ~25 instructions per pixel).  Here one thread produces FOUR adjacent output
+// pixels of a row -- one 32-bit store, 128 contiguous bytes per warp -- the column terms (two window offsets, u, 1-u)
+// of its four columns stay in registers for all rows of the tile, the row terms come from a small shared table, the
+// source window is fetched with aligned 32-bit loads (four texels each) and decoded once into shared memory, and the
+// arithmetic runs on column pairs with packed fp32 (products only: the additions stay scalar so that ptxas cannot
+// contract them into FMAs -- every pixel keeps the oracle's two roundings per term, bit for bit).
+constexpr int kFastCols = 512, kFastRows = 32, kFastThreads = 128;
+constexpr int kFastWin = 10240;               // floats (40 KB) of decoded window
+
+struct FastRow { int ya, yb; float omv, v; };  // window-relative byte offsets of the two source rows, y weights
+
+// upper bound of the decoded window of one tile, in floats (dynamic shared memory of the launch)
+inline long long resize_fast_win_floats(const ResizeParams& p)
+{
+    const long long ww = ((long long)kFastCols * p.sw / p.dw + 12 + 3) / 4 * 4, wh = (long long)kFastRows * p.sh / p.dh + 5;
+    return ww * wh;
+}
+
+// host-side eligibility: gray, bilinear mode, 4-byte aligned rows on both sides, window of a tile fits
+inline bool resize_fast_ok(const ResizeParams& p)
+{
+    if (p.channels != 1 || p.mode == 1) return false;
+    if (((reinterpret_cast<uintptr_t>(p.src) | p.src_pitch | p.src_frame_stride | reinterpret_cast<uintptr_t>(p.dst) | p.dst_pitch | p.dst_frame_stride) & 3) != 0) return false;
+    if (p.dw < 4) return false;
+    return resize_fast_win_floats(p) <= kFastWin;
+}
+
+__global__ void __launch_bounds__(kFastThreads) resize_bilinear_gray_kernel(const ResizeParams p)
+{
+    extern __shared__ __align__(16) float win[];               // resize_fast_win_floats(p) floats
+    __shared__ float lut[256];
+    __shared__ __align__(16) FastRow rowt[kFastRows];
+    __shared__ int wbox[4];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * kFastCols + 4 * tid, y0 = blockIdx.y * kFastRows;
+    const int rows = min(kFastRows, p.dh - y0);
+    lut[tid] = __fdiv_rn((float)tid, 255.0f);
+    lut[tid + 128] = __fdiv_rn((float)(tid + 128), 255.0f);
+    auto map = [&](int i, int nd, int ns) {     // interpolation.cl:58-69 (mode 0) / the normalised sampler (mode 2)
+        return p.mode == 2 ? __fsub_rn(__fmul_rn(__fdiv_rn((float)i, (float)(nd - 1)), (float)ns), 0.5f)
+                           : __fmul_rn(__fdiv_rn((float)i, (float)(nd - 1)), (float)(ns - 1));
+    };
+    int ya_abs = 0, yb_abs = 0;
+    float vrow = 0.0f;
+    if (tid < kFastRows) {
+        const float fy = map(min(y0 + tid, p.dh - 1), p.dh, p.sh);
+        const float fl = floorf(fy);
+        ya_abs = min(max((int)fl, 0), p.sh - 1); yb_abs = min(max((int)fl + 1, 0), p.sh - 1);
+        vrow = __fsub_rn(fy, fl);
+        if (tid == 0) wbox[2] = ya_abs;
+        if (tid == rows - 1) wbox[3] = yb_abs;
+    }
+    int xa[4], xb[4];
+    float u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float fx = map(min(x0 + k, p.dw - 1), p.dw, p.sw);
+        const float fl = floorf(fx);
+        xa[k] = min(max((int)fl, 0), p.sw - 1); xb[k] = min(max((int)fl + 1, 0), p.sw - 1);
+        u[k] = __fsub_rn(fx, fl);
+    }
+    if (tid == 0) wbox[0] = xa[0] & ~3;                       // the window starts on a 4-byte boundary of the source row
+    if (tid == kFastThreads - 1) wbox[1] = xb[3];             // clamped indices are monotone in x
+    __syncthreads();
+    const int wx0 = wbox[0], ww4 = (wbox[1] - wx0) / 4 + 1;   // words (4 texels) per window row
+    const int wy0 = wbox[2], wh = wbox[3] - wy0 + 1;
+    const int wpitch = 4 * ww4;                               // floats per window row
+    if (tid < kFastRows) rowt[tid] = FastRow{(ya_abs - wy0) * wpitch * 4, (yb_abs - wy0) * wpitch * 4, __fsub_rn(1.0f, vrow), vrow};
+    const uint8_t* src = p.src + (size_t)blockIdx.z * p.src_frame_stride + (size_t)wy0 * p.src_pitch + wx0;
+    for (int r = 0; r < wh; r += 4) {                          // four rows per pass: their loads are in flight together
+        for (int c = tid; c < ww4; c += kFastThreads) {
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                w[k] = (r + k < wh) ? __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)(r + k) * p.src_pitch) + c) : 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (r + k < wh)
+                    *reinterpret_cast<float4*>(&win[(r + k) * wpitch + 4 * c]) =
+                        make_float4(lut[w[k] & 0xffu], lut[(w[k] >> 8) & 0xffu], lut[(w[k] >> 16) & 0xffu], lut[w[k] >> 24]);
+        }
+    }
+    __syncthreads();
+    if (x0 >= p.dw) return;
+    int oa[4], ob[4];                                          // window-relative byte offsets of the two taps of each column
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { oa[k] = 4 * (xa[k] - wx0); ob[k] = 4 * (xb[k] - wx0); }
+    const p2 U01 = pk(u[0], u[1]), U23 = pk(u[2], u[3]);
+    const p2 OMU01 = pk(__fsub_rn(1.0f, u[0]), __fsub_rn(1.0f, u[1])), OMU23 = pk(__fsub_rn(1.0f, u[2]), __fsub_rn(1.0f, u[3]));
+    const bool full = x0 + 3 < p.dw;
+    uint8_t* drow = p.dst + (size_t)blockIdx.z * p.dst_frame_stride + (size_t)y0 * p.dst_pitch + x0;
+    const char* wbase = reinterpret_cast<const char*>(win);
+    auto W = [&](int off) { return *reinterpret_cast<const float*>(wbase + off); };
+    // Texels of the two source rows of the current output row, for the thread's four columns (.lo/.hi = column pairs).
+    // Consecutive output rows mostly use the same source rows, or the lower one becomes the upper one: the row table
+    // is the same for the whole CTA, so these are uniform branches and an up-scale by s loads 2/s texels per pixel.
+    p2 ta01 = 0, tb01 = 0, ta23 = 0, tb23 = 0;      // upper row: taps a (x0) and b (x1)
+    p2 ba01 = 0, bb01 = 0, ba23 = 0, bb23 = 0;      // lower row
+    auto load_row = [&](int yoff, p2& a01, p2& b01, p2& a23, p2& b23) {
+        a01 = pk(W(yoff + oa[0]), W(yoff + oa[1])); b01 = pk(W(yoff + ob[0]), W(yoff + ob[1]));
+        a23 = pk(W(yoff + oa[2]), W(yoff + oa[3])); b23 = pk(W(yoff + ob[2]), W(yoff + ob[3]));
+    };
+    auto blend = [&](p2 OMU, p2 U, p2 OMV, p2 V, p2 ta, p2 tb, p2 ba, p2 bb, unsigned& q0, unsigned& q1) {
+        float l0, h0, l1, h1;
+        upk(mul2(mul2(OMU, OMV), ta), l0, h0);
+        upk(mul2(mul2(U, OMV), tb), l1, h1);
+        float accl = __fadd_rn(l0, l1), acch = __fadd_rn(h0, h1);
+        upk(mul2(mul2(OMU, V), ba), l0, h0);
+        accl = __fadd_rn(accl, l0); acch = __fadd_rn(acch, h0);
+        upk(mul2(mul2(U, V), bb), l0, h0);
+        accl = __fadd_rn(accl, l0); acch = __fadd_rn(acch, h0);
+        // write_imagef to UNORM_INT8: saturate, x255, round to nearest even.  A bilinear blend of [0,1] texels is never
+        // negative and at most an ulp above 1, which rounds to 255 like the clamped value: no explicit clamp needed.
+        q0 = __float2uint_rn(__fmul_rn(accl, 255.0f));
+        q1 = __float2uint_rn(__fmul_rn(acch, 255.0f));
+    };
+    int cur_ya = -1, cur_yb = -1;
+    for (int r = 0; r < rows; ++r) {
+        const FastRow rt = rowt[r];
+        if (rt.ya != cur_ya || rt.yb != cur_yb) {
+            if (rt.ya == cur_yb) { ta01 = ba01; tb01 = bb01; ta23 = ba23; tb23 = bb23; }
+            else if (rt.ya != cur_ya) load_row(rt.ya, ta01, tb01, ta23, tb23);
+            if (rt.yb == rt.ya) { ba01 = ta01; bb01 = tb01; ba23 = ta23; bb23 = tb23; }
+            else load_row(rt.yb, ba01, bb01, ba23, bb23);
+            cur_ya = rt.ya; cur_yb = rt.yb;
+        }
+        const p2 OMV = bc(rt.omv), V = bc(rt.v);
+        unsigned q0, q1, q2, q3;
+        blend(OMU01, U01, OMV, V, ta01, tb01, ba01, bb01, q0, q1);
+        blend(OMU23, U23, OMV, V, ta23, tb23, ba23, bb23, q2, q3);
+        uint8_t* d = drow + (size_t)r * p.dst_pitch;
+        if (full) {
+            *reinterpret_cast<uint32_t*>(d) = __byte_perm(__byte_perm(q0, q1, 0x0040), __byte_perm(q2, q3, 0x0040), 0x5410);
+        } else {
+            d[0] = (uint8_t)q0;
+            if (x0 + 1 < p.dw) d[1] = (uint8_t)q1;
+            if (x0 + 2 < p.dw) d[2] = (uint8_t)q2;
+        }
+    }
 }
 
 }  // namespace raisr
