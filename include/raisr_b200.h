@@ -92,7 +92,7 @@ int raisr_set_stream(raisr_t* h, void* cuda_stream);
  *               ma accumulates gx*gy (raisr.cl:271), the coherence bucket compares L1 (raisr.cl:310),
  *               strength is left out of the hash (raisr.cl:316)
  *   "cheap_upscaler" 1 = stage 1 uses the reference's cubic_sample (raisr.cl:63-106, present in the kernel
- *               source but never called) instead of linear_sample; gray path only
+ *               source but never called) instead of linear_sample; gray and colour paths (packed prep kernel only)
  *   "taps"      precision of the taps in the resident shared-memory table; arithmetic is fp32 in every mode.
  *               0 = fp32.  1 = fp16, as the reference's `(half)pf[...]` (raisr.cl:328) does.  2 = b24: sign, exponent
  *               and 15 mantissa bits (three quarters of the tap stream that bounds the filter kernel).  3 = auto

@@ -575,6 +575,7 @@ int raisr_set_option(raisr_t* h, const char* key, long long value)
         return 0;
     }
     if (!strcmp(key, "prep_impl")) { h->prep_impl = value == 1 ? 1 : 2; return 0; }
+    if (!strcmp(key, "filter_duo")) { h->duo = value ? 1 : 0; return 0; }
     if (!strcmp(key, "resize_fast")) { h->resize_fast = value ? 1 : 0; return 0; }
     if (!strcmp(key, "filter_pipe")) { h->filter_pipe = value ? 1 : 0; return 0; }
     if (!strcmp(key, "color_filter_impl")) { h->color_filter_impl = value == 1 ? 1 : 2; return 0; }
@@ -667,7 +668,7 @@ static int enqueue_bgra_frame(raisr_ctx* h, const Geometry& g, const uint8_t* ds
     const size_t fpitch = round_up((size_t)dw, 4), fplane = fpitch * dh;
     ColorUpParams cu{};
     cu.src = dsrc; cu.src_pitch = src_pitch;
-    cu.sw = sw; cu.sh = sh; cu.dw = dw; cu.dh = dh; cu.pitch = g.uext_pitch;
+    cu.sw = sw; cu.sh = sh; cu.dw = dw; cu.dh = dh; cu.pitch = g.uext_pitch; cu.cubic = h->cubic;
     for (int k = 0; k < 4; ++k) cu.plane[k] = (float*)h->uext.p + g.uext_frame * k;
     dim3 gu((dw + 2 * kMargin + 255) / 256, (dh + 2 * kMargin + 3) / 4);
     color_upscale_kernel<<<gu, 256, 0, st>>>(cu);
@@ -677,6 +678,7 @@ static int enqueue_bgra_frame(raisr_ctx* h, const Geometry& g, const uint8_t* ds
     FilterParams fp;
     fill_params(h, g, dsrc, sw, sh, src_pitch, h->cplanes.p, fpitch * sizeof(float), scale, 0, 1, (float*)h->uext.p, (uint8_t*)h->hash.p, pp, fp);
     pp.uext_in = (const float*)h->uext.p;   // Y plane
+    pp.cubic = 0;                            // stage 1 already happened (color_upscale_kernel); the hash stage reads the plane
     if (int rc = launch_prep(h, pp, scale, st, false)) return rc;
     fp.raw_f32 = 1;
     bool done = false;
@@ -1054,7 +1056,7 @@ int raisr_debug_hash_bgra(raisr_t* h, const uint8_t* src, int sw, int sh, size_t
     h->scratch_acquire(st);
     ColorUpParams cu{};
     cu.src = dsrc; cu.src_pitch = src_pitch;
-    cu.sw = sw; cu.sh = sh; cu.dw = dw; cu.dh = dh; cu.pitch = g.uext_pitch;
+    cu.sw = sw; cu.sh = sh; cu.dw = dw; cu.dh = dh; cu.pitch = g.uext_pitch; cu.cubic = h->cubic;
     for (int k = 0; k < 4; ++k) cu.plane[k] = (float*)h->uext.p + g.uext_frame * k;
     dim3 gu((dw + 2 * kMargin + 255) / 256, (dh + 2 * kMargin + 3) / 4);
     color_upscale_kernel<<<gu, 256, 0, st>>>(cu);
@@ -1064,6 +1066,7 @@ int raisr_debug_hash_bgra(raisr_t* h, const uint8_t* src, int sw, int sh, size_t
     FilterParams fp;
     fill_params(h, g, dsrc, sw, sh, src_pitch, nullptr, 0, scale, 0, 1, (float*)h->uext.p, (uint8_t*)h->hash.p, pp, fp);
     pp.uext_in = (const float*)h->uext.p;   // Y plane
+    pp.cubic = 0;
     pp.dbg_hash = (int32_t*)dev[0]; pp.dbg_angle = (float*)dev[1]; pp.dbg_l1 = (float*)dev[2]; pp.dbg_coh = (float*)dev[3];
     pp.dbg_pitch = dw;
     if (int rc = launch_prep(h, pp, scale, st, true)) return rc;

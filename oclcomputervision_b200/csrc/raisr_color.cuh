@@ -24,6 +24,7 @@ struct ColorUpParams {
     int sw, sh, dw, dh;
     float* plane[4];                         // Y,U,V,A uext planes
     size_t pitch;                            // floats per column
+    int cubic;                               // 1 = the reference's cubic_sample (raisr.cl:63-106, a half4 routine) instead of linear_sample
 };
 
 __constant__ float kCscToYuv[16] = {0.299f, 0.587f, 0.114f, 0.0f, -0.14713f, -0.28886f, 0.436f, 0.0f,
@@ -53,6 +54,51 @@ __global__ void __launch_bounds__(256) color_upscale_kernel(const ColorUpParams 
     const float u = __fsub_rn(fx, flx), omu = __fsub_rn(1.0f, u);
     const int x0 = min(max(xi, 0), p.sw - 1), x1 = min(max(xi + 1, 0), p.sw - 1);
     float out[4][4];
+    if (p.cubic) {
+        // cubic_sample (raisr.cl:63-106): 4x4 taps around floor(coord), w_k = dot((1,u,u2,u3), cubic_matrix[k]) left to
+        // right, acc += (pix * xweight[j]) * yweight[i] with i outer / j inner, every channel clamped to [0,1]
+        auto weights = [](float t, float (&w)[4]) {
+            const float t2 = __fmul_rn(t, t), t3 = __fmul_rn(t2, t);
+            auto dot = [&](float m0, float m1, float m2, float m3) {
+                float acc = __fadd_rn(__fmul_rn(1.0f, m0), __fmul_rn(t, m1));
+                acc = __fadd_rn(acc, __fmul_rn(t2, m2));
+                return __fadd_rn(acc, __fmul_rn(t3, m3));
+            };
+            w[0] = dot(0.0f, -0.5f, 1.0f, -0.5f); w[1] = dot(1.0f, 0.0f, -2.5f, 1.5f);
+            w[2] = dot(0.0f, 0.5f, 2.0f, -1.5f);  w[3] = dot(0.0f, 0.0f, -0.5f, 0.5f);
+        };
+        float xw[4];
+        weights(u, xw);
+        int xs[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xs[j] = min(max(xi - 1 + j, 0), p.sw - 1);
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            const int er = er0 + k;
+            const float fy = __fmul_rn(__fdiv_rn((float)(er - kMargin), (float)(p.dh - 1)), (float)(p.sh - 1));
+            const float fly = floorf(fy);
+            const int yi = (int)fly;
+            float yw[4];
+            weights(__fsub_rn(fy, fly), yw);
+            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};      // B, G, R, A
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uchar4* row = reinterpret_cast<const uchar4*>(p.src + (size_t)min(max(yi - 1 + i, 0), p.sh - 1) * p.src_pitch);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uchar4 q = __ldg(row + xs[j]);
+                    const unsigned char ch[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        acc[c] = __fadd_rn(acc[c], __fmul_rn(__fmul_rn(__fdiv_rn((float)ch[c], 255.0f), xw[j]), yw[i]));
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[c] = fminf(fmaxf(acc[c], 0.0f), 1.0f);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) out[c][k] = dot4_rn(kCscToYuv + 4 * c, acc[2], acc[1], acc[0], acc[3]);
+        }
+    } else
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int er = er0 + k;

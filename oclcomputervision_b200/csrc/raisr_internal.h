@@ -109,6 +109,7 @@ struct raisr_ctx {
     int prep_impl = 2;    // 2 = packed-fp32 prep2_kernel, 1 = scalar prep_kernel
     int filter_pipe = 1;        // 1 = mbarrier full/empty tile pipeline with a producer warp (default), 0 = CTA-wide barriers per tile
     int color_filter_impl = 2;  // 2 = two planes per CTA (s = 2, fp32 taps), 1 = one launch per plane
+    int duo = 1;          // "filter_duo": 1 = two pixel types per CTA for s = 2 with b24 records (default), 0 = one type per CTA
     int resize_fast = 1;  // 1 = four-pixels-per-thread kernel for gray bilinear resizes that qualify (default), 0 = generic kernel
     int cubic = 0;        // "cheap_upscaler" option: 1 = bicubic stage 1 (gray path, prep2 kernel)
     int as_written = 0;   // "quirks" option
@@ -133,5 +134,9 @@ struct raisr_ctx {
 int raisr_launch_prep(raisr_ctx* h, const raisr::PrepParams& p, int s, cudaStream_t st, bool dbg, int ctas_per_sm);
 int raisr_launch_filter_u8(raisr_ctx* h, raisr::FilterParams p, int s, cudaStream_t st, bool single_buffer, bool allow_b24);
 int raisr_launch_filter_f32(raisr_ctx* h, raisr::FilterParams p, int s, cudaStream_t st, bool single_buffer, bool allow_b24);
+// s = 2 with 24-bit tap records: both pixel types of an output row per CTA (raisr_duo.cuh); p.table = the b24 table.
+// Returns 1 when the kernel cannot be used for this call (the caller falls back to the one-type kernel).
+int raisr_launch_duo_u8(raisr_ctx* h, raisr::FilterParams p, cudaStream_t st);
+int raisr_launch_duo_f32(raisr_ctx* h, raisr::FilterParams p, cudaStream_t st);
 // colour path, s = 2, fp32 taps: all four planes in one launch (returns 1 when the kernel does not fit: fall back per plane)
 int raisr_launch_filter_octet2(raisr_ctx* h, raisr::FilterParams p, cudaStream_t st);

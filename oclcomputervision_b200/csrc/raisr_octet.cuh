@@ -23,6 +23,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include "packed_f32.cuh"
 #include "raisr_filter.cuh"
 
 namespace raisr {
@@ -498,14 +499,29 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1)
                         lds128_if(q1, tpa + 128, reload);
                         const float c11 = W(q2.x, q2.y, 0x4321), c12 = __uint_as_float(q2.y), c13 = W(q2.y, q2.z, 0x6543), c14 = W(q2.z, q2.w, 0x5432);
                         lds128_if(q2, tpa + 256, reload);
-                        a0 = w11[(o + 0) % G::WF] * c0; a1 = w11[(o + 1) % G::WF] * c1;
-                        a0 = fmaf(w11[(o + 2) % G::WF], c2, a0); a1 = fmaf(w11[(o + 3) % G::WF], c3, a1);
-                        a0 = fmaf(w11[(o + 4) % G::WF], c4, a0); a1 = fmaf(w11[(o + 5) % G::WF], c5, a1);
-                        a0 = fmaf(w11[(o + 6) % G::WF], c6, a0); a1 = fmaf(w11[(o + 7) % G::WF], c7, a1);
-                        a0 = fmaf(w11[(o + 8) % G::WF], c8, a0); a1 = fmaf(w11[(o + 9) % G::WF], c9, a1);
-                        a0 = fmaf(w11[(o + 10) % G::WF], c10, a0); a1 = fmaf(w5[(o + 0) & MP], c11, a1);
-                        a0 = fmaf(w5[(o + 1) & MP], c12, a0); a1 = fmaf(w5[(o + 2) & MP], c13, a1);
-                        a0 = fmaf(w5[(o + 3) & MP], c14, a0); a1 = fmaf(w5[(o + 4) & MP], c15, a1);
+                        // Two chains, summed at the end: chain 0 takes slots 0,2,4,6,8,11,13 and then 10, chain 1 slots
+                        // 1,3,5,7,9,12,14 and then 15.  For even S the window offset o = S*b is even, so (slot 2m, slot 2m+1)
+                        // of both windows are fixed register pairs and seven of the nine steps are packed FFMA2 (two IEEE
+                        // fp32 FMAs per issue slot; the kernel is bound by issue slots, the FMA pipe is a third busy).
+                        if (S % 2 == 0) {
+                            p2 acc2 = mul2(pk(w11[(o + 0) % G::WF], w11[(o + 1) % G::WF]), pk(c0, c1));
+                            acc2 = fma2(pk(w11[(o + 2) % G::WF], w11[(o + 3) % G::WF]), pk(c2, c3), acc2);
+                            acc2 = fma2(pk(w11[(o + 4) % G::WF], w11[(o + 5) % G::WF]), pk(c4, c5), acc2);
+                            acc2 = fma2(pk(w11[(o + 6) % G::WF], w11[(o + 7) % G::WF]), pk(c6, c7), acc2);
+                            acc2 = fma2(pk(w11[(o + 8) % G::WF], w11[(o + 9) % G::WF]), pk(c8, c9), acc2);
+                            acc2 = fma2(pk(w5[(o + 0) & MP], w5[(o + 1) & MP]), pk(c11, c12), acc2);
+                            acc2 = fma2(pk(w5[(o + 2) & MP], w5[(o + 3) & MP]), pk(c13, c14), acc2);
+                            upk(acc2, a0, a1);
+                        } else {
+                            a0 = w11[(o + 0) % G::WF] * c0; a1 = w11[(o + 1) % G::WF] * c1;
+                            a0 = fmaf(w11[(o + 2) % G::WF], c2, a0); a1 = fmaf(w11[(o + 3) % G::WF], c3, a1);
+                            a0 = fmaf(w11[(o + 4) % G::WF], c4, a0); a1 = fmaf(w11[(o + 5) % G::WF], c5, a1);
+                            a0 = fmaf(w11[(o + 6) % G::WF], c6, a0); a1 = fmaf(w11[(o + 7) % G::WF], c7, a1);
+                            a0 = fmaf(w11[(o + 8) % G::WF], c8, a0); a1 = fmaf(w11[(o + 9) % G::WF], c9, a1);
+                            a0 = fmaf(w5[(o + 0) & MP], c11, a0); a1 = fmaf(w5[(o + 1) & MP], c12, a1);
+                            a0 = fmaf(w5[(o + 2) & MP], c13, a0); a1 = fmaf(w5[(o + 3) & MP], c14, a1);
+                        }
+                        a0 = fmaf(w11[(o + 10) % G::WF], c10, a0); a1 = fmaf(w5[(o + 4) & MP], c15, a1);
                     } else if (H16) {
                         float2 c0 = h2f2(q0.x), c1 = h2f2(q0.y), c2 = h2f2(q0.z), c3 = h2f2(q0.w);
                         lds128_if(q0, tpa, reload);

@@ -308,7 +308,7 @@ def _load():
         lib.raisr_oracle_run_bgra.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_int, vp, ctypes.c_int,
                                               ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int]
         lib.raisr_oracle_run_bgra_ex.restype = ctypes.c_int
-        lib.raisr_oracle_run_bgra_ex.argtypes = list(lib.raisr_oracle_run_bgra.argtypes) + [vp, vp, vp]
+        lib.raisr_oracle_run_bgra_ex.argtypes = list(lib.raisr_oracle_run_bgra.argtypes) + [vp, vp, vp, ctypes.c_int]
         lib.raisr_oracle_resize_u8.restype = ctypes.c_int
         lib.raisr_oracle_resize_u8.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_int, vp,
                                                ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_int]
@@ -392,8 +392,11 @@ def resize_u8_c(src: np.ndarray, out_hw, mode: str) -> np.ndarray:
 
 
 def raisr_ref_bgra_c(src_bgra: np.ndarray, filters: np.ndarray, s: int = 2, *, n_angle=24, n_strength=3, n_coherence=3,
-                     strength_q=DEFAULT_STRENGTH_Q, coherence_q=DEFAULT_COHERENCE_Q, nthreads: int = 0) -> Dict[str, np.ndarray]:
-    """C restatement of the colour (BGRA) path (raisr_oracle.c: raisr_oracle_run_bgra)."""
+                     strength_q=DEFAULT_STRENGTH_Q, coherence_q=DEFAULT_COHERENCE_Q, nthreads: int = 0,
+                     upscaler: str = "bilinear") -> Dict[str, np.ndarray]:
+    """C restatement of the colour (BGRA) path (raisr_oracle.c: raisr_oracle_run_bgra).  upscaler="bicubic": stage 1 is
+    the reference's cubic_sample (raisr.cl:63-106) on each of the four channels."""
+    assert upscaler in ("bilinear", "bicubic")
     lib = _load()
     src = np.ascontiguousarray(src_bgra, dtype=np.uint8)
     assert src.ndim == 3 and src.shape[2] == 4
@@ -407,7 +410,7 @@ def raisr_ref_bgra_c(src_bgra: np.ndarray, filters: np.ndarray, s: int = 2, *, n
     rc = lib.raisr_oracle_run_bgra_ex(src.ctypes.data, sw, sh, src.strides[0], s, flt.ctypes.data, n_angle, n_strength, n_coherence,
                                       sq.ctypes.data, cq.ctypes.data, res["hash"].ctypes.data, res["out_f32"].ctypes.data,
                                       res["out_u8"].ctypes.data, int(nthreads), res["angle"].ctypes.data, res["L1"].ctypes.data,
-                                      res["coherence"].ctypes.data)
+                                      res["coherence"].ctypes.data, int(upscaler == "bicubic"))
     if rc != 0:
         raise RuntimeError("raisr_oracle_run_bgra failed (%d)" % rc)
     return res

@@ -254,3 +254,26 @@ def test_device_then_host_calls_share_scratch_safely():
         tdst.zero_()
     r.set_stream(0)
     r.close()
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (3, 200), (37, 53), (130, 67), (270, 480), (64, 65)])
+def test_duo_kernel_equals_one_type_kernel(shape):
+    """s = 2 with 24-bit records runs the two-types-per-CTA kernel (csrc/raisr_duo.cuh, `filter_duo` = 1, default); it
+    keeps the per-pixel accumulation order of filter_octet_kernel, so u8 and float outputs are bit-identical to the
+    one-type kernel (`filter_duo` = 0) -- single frames, ragged sizes and batches that span several tiles per worker."""
+    flt = synth.random_filters(2, seed=17)
+    n = 3
+    frames = np.stack([synth.synthetic_frame(max(shape[0], 8), max(shape[1], 8), seed=400 + k)[:shape[0], :shape[1]] for k in range(n)]).copy()
+    outs = []
+    for duo in (1, 0):
+        r = ClRaisr(1, filters=flt, device=0)
+        assert r.effective_filters(2)[1] == "b24"
+        r.set_option("filter_duo", duo)
+        dst = np.empty((n, 2 * shape[0], 2 * shape[1]), np.uint8)
+        r.upsample_batch(frames, dst, 2)
+        dstf = np.empty((n, 2 * shape[0], 2 * shape[1]), np.float32)
+        r.upsample_batch(frames, dstf, 2)
+        outs.append((dst, dstf))
+        r.close()
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1])

@@ -382,9 +382,22 @@ def test_bicubic_cheap_upscaler_against_oracle(shape, s):
     with pytest.raises(_cabi.RaisrError):
         r.upsample(src, dst, s)
     r.close()
-    c = ClRaisr(0, filters=synth.random_filters(2), device=0, upscaler="bicubic")
-    with pytest.raises(_cabi.RaisrError):
-        c.upsample(np.zeros((8, 8, 4), np.uint8), np.zeros((16, 16, 4), np.uint8), 2)
+    # colour mode: cubic_sample is a half4 routine in the reference (raisr.cl:63-106), all four channels go through it
+    rng = np.random.default_rng(shape[0])
+    bgra = np.stack([synth.synthetic_frame(shape[0], shape[1], seed=60 + k) for k in range(3)] +
+                    [rng.integers(180, 256, shape, dtype=np.uint8)], axis=2).copy()
+    cw = O.raisr_ref_bgra_c(bgra, flt, s, upscaler="bicubic")
+    assert not np.array_equal(cw["out_u8"], O.raisr_ref_bgra_c(bgra, flt, s)["out_u8"])
+    c = ClRaisr(0, device=0, upscaler="bicubic")
+    setattr(c, "filters_x%d" % s, flt)
+    ch, cang, cl1, ccoh, _ = c.debug_hash(bgra, s)
+    assert np.array_equal(cl1, cw["L1"]) and np.array_equal(ccoh, cw["coherence"])
+    cbad = ch != cw["hash"]
+    assert not (cbad & ~(O.edge_distance(cw) < 1e-5)).any()
+    assert np.abs(c.upsample_f32(bgra, s) - cw["out_f32"]).max(axis=2)[~cbad].max() <= 1e-4
+    cdst = np.empty((shape[0] * s, shape[1] * s, 4), np.uint8)
+    c.upsample(bgra, cdst, s)
+    assert np.abs(cdst.astype(int) - cw["out_u8"].astype(int)).max(axis=2)[~cbad].max() <= 1
     c.close()
 
 
