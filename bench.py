@@ -559,8 +559,10 @@ def main():
         chunk_mb = args.chunk_mb or 208
         chunk_frames = max(1, min(n, int((chunk_mb << 20) // (((dh + 18 + 3) // 4 * 4) * (dw + 10) * 4))))   # frames per kernel launch (as in raisr_api.cu)
         launches_per_step = 2 * ((n + chunk_frames - 1) // chunk_frames)
-        prof = ncu_metrics("filter_octet_kernel", tap_format)
-        dom = dict(name="filter_octet_kernel<%s taps>" % tap_format, flop_per_px=FLOP_PER_PX_FILTER,
+        # s = 2 with 24-bit records runs the two-types-per-CTA kernel unless --duo 0
+        kname = "filter_duo_kernel" if (tap_format == "b24" and args.duo in (None, 1)) else "filter_octet_kernel"
+        prof = ncu_metrics(kname, tap_format)
+        dom = dict(name="%s<%s taps>" % (kname, tap_format), flop_per_px=FLOP_PER_PX_FILTER,
                    achieved_tflops=round(FLOP_PER_PX_FILTER * px_total / filt_s / 1e12, 3),
                    avg_launch_ms=round(filt_ms / (args.steps * launches_per_step / 2), 4),
                    binding_resource="shared-memory data pipe, 1 wavefront (128 B) per clock per SM: each pixel needs its own 121 taps")
