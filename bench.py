@@ -557,7 +557,11 @@ def main():
         filt_s = filt_ms * 1e-3
         px_total = px_per_step * args.steps
         chunk_mb = args.chunk_mb or 208
-        chunk_frames = max(1, min(n, int((chunk_mb << 20) // (((dh + 18 + 3) // 4 * 4) * (dw + 10) * 4))))   # frames per kernel launch (as in raisr_api.cu)
+        per_frame_bytes = ((dh + 18 + 3) // 4 * 4) * (dw + 10) * 4
+        chunk_frames = (chunk_mb << 20) // per_frame_bytes                      # frames per kernel launch (frames_per_launch() of raisr_api.cu)
+        if chunk_frames < 3 and chunk_mb >= 200:
+            chunk_frames = min(3, (2 << 30) // per_frame_bytes)
+        chunk_frames = max(1, min(n, int(chunk_frames)))
         launches_per_step = 2 * ((n + chunk_frames - 1) // chunk_frames)
         # s = 2 with 24-bit records runs the two-types-per-CTA kernel unless --duo 0
         kname = "filter_duo_kernel" if (tap_format == "b24" and args.duo in (None, 1)) else "filter_octet_kernel"

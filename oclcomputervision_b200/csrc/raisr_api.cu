@@ -150,6 +150,17 @@ void fill_params(raisr_ctx* h, const Geometry& g, const uint8_t* dsrc, int sw, i
     fp.ow = sw; fp.oh = sh; fp.n_frames = n;
 }
 
+// Frames per kernel launch: what the scratch budget holds, but at least three (memory permitting: up to 2 GiB of
+// scratch) -- a launch of one 8K frame is 21.1 waves of prep tiles, i.e. 4 % of it is a half-empty last wave
+// (4K->8K: 37.2 -> 38.2 Gpix/s with three frames per launch; larger launches lengthen the fill / drain of the HOST pipeline).
+int frames_per_launch(const raisr_ctx* h, size_t per_frame, int nf)
+{
+    per_frame = std::max<size_t>(per_frame, 1);
+    size_t n = h->chunk_budget / per_frame;
+    if (n < 3 && h->chunk_budget >= (200u << 20)) n = std::min<size_t>(3, ((size_t)2 << 30) / per_frame);
+    return (int)std::max<size_t>(1, std::min<size_t>((size_t)nf, n));
+}
+
 // Enqueue prep+filter for `nf` frames that are already on the device.  Event slots used (relative to
 // ev_base): 3 per chunk in the serial pipeline; the overlapped pipeline uses 4 per chunk + 2.
 template <typename OutT>
@@ -158,7 +169,7 @@ int enqueue_frames(raisr_ctx* h, const uint8_t* dsrc, int sw, int sh, size_t src
 {
     Geometry g = make_geometry(sw, sh * scale, scale);
     size_t per_frame = g.uext_frame * sizeof(float);
-    int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nf, h->chunk_budget / std::max<size_t>(per_frame, 1)));
+    int chunk = frames_per_launch(h, per_frame, nf);
     if (int rc = h->uext.ensure(per_frame * chunk)) return rc;
     if (int rc = h->hash.ensure_zero(g.hash_frame * chunk)) return rc;
     const int nchunks = (nf + chunk - 1) / chunk;
@@ -259,7 +270,7 @@ int upsample_impl(raisr_ctx* h, const uint8_t* src, int sw, int sh, size_t src_p
     const size_t src_frame = src_pitch * sh, dst_frame = dst_pitch * dh;
     Geometry g = make_geometry(sw, dh, scale);
     size_t per_frame = g.uext_frame * sizeof(float);
-    int dev_chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_frames, h->chunk_budget / std::max<size_t>(per_frame, 1)));
+    int dev_chunk = frames_per_launch(h, per_frame, n_frames);
     // with the overlapped kernel pipeline a host chunk spans several device chunks so that it has something to overlap
     int chunk = std::min(n_frames, h->overlap ? dev_chunk * 4 : dev_chunk);
     for (int b = 0; b < 2; ++b) {
@@ -273,10 +284,14 @@ int upsample_impl(raisr_ctx* h, const uint8_t* src, int sw, int sh, size_t src_p
     {
         int left = n_frames;
         std::vector<int> tail;
-        if (!h->overlap && chunk >= 4 && n_frames >= 3 * chunk) {
+        if (!h->overlap && chunk >= 3 && n_frames >= 3 * chunk) {
             sizes = {1, 2};
             tail = {2, 1};
             left -= 6;
+        } else if (!h->overlap && chunk == 2 && n_frames >= 6) {
+            sizes = {1};
+            tail = {1};
+            left -= 2;
         }
         while (left > 0) { const int n = std::min(chunk, left); sizes.push_back(n); left -= n; }
         sizes.insert(sizes.end(), tail.begin(), tail.end());
