@@ -212,7 +212,7 @@ int enqueue_frames(raisr_ctx* h, const uint8_t* dsrc, int sw, int sh, size_t src
         fill_params(h, g, dsrc, sw, sh, src_pitch, ddst, dst_pitch, scale, f0, n, (float*)h->uext.p, (uint8_t*)h->hash.p, pp, fp);
         size_t e = ev_base + 3 * (size_t)(f0 / chunk);
         if (timed) cudaEventRecord(h->ev(e), st);
-        if (int rc = launch_prep(h, pp, scale, st, false)) return rc;
+        if (int rc = launch_prep(h, pp, scale, st, false, h->prep_ctas_per_sm)) return rc;
         if (timed) cudaEventRecord(h->ev(e + 1), st);
         if (int rc = launch_filter<OutT>(h, fp, scale, st)) return rc;
         if (timed) cudaEventRecord(h->ev(e + 2), st);
@@ -590,6 +590,7 @@ int raisr_set_option(raisr_t* h, const char* key, long long value)
         return 0;
     }
     if (!strcmp(key, "prep_impl")) { h->prep_impl = value == 1 ? 1 : 2; return 0; }
+    if (!strcmp(key, "prep_ctas_per_sm")) { h->prep_ctas_per_sm = (int)std::max<long long>(0, std::min<long long>(value, 8)); return 0; }
     if (!strcmp(key, "filter_duo")) { h->duo = value ? 1 : 0; return 0; }
     if (!strcmp(key, "resize_fast")) { h->resize_fast = value ? 1 : 0; return 0; }
     if (!strcmp(key, "filter_pipe")) { h->filter_pipe = value ? 1 : 0; return 0; }

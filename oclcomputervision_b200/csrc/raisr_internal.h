@@ -109,6 +109,7 @@ struct raisr_ctx {
     int prep_impl = 2;    // 2 = packed-fp32 prep2_kernel, 1 = scalar prep_kernel
     int filter_pipe = 1;        // 1 = mbarrier full/empty tile pipeline with a producer warp (default), 0 = CTA-wide barriers per tile
     int color_filter_impl = 2;  // 2 = two planes per CTA (s = 2, fp32 taps), 1 = one launch per plane
+    int prep_ctas_per_sm = 0;   // 0 = one prep CTA per tile (default), n > 0 = persistent grid of n CTAs per SM striding over the tiles
     int duo = 1;          // "filter_duo": 1 = two pixel types per CTA for s = 2 with b24 records (default), 0 = one type per CTA
     int resize_fast = 1;  // 1 = four-pixels-per-thread kernel for gray bilinear resizes that qualify (default), 0 = generic kernel
     int cubic = 0;        // "cheap_upscaler" option: 1 = bicubic stage 1 (gray path, prep2 kernel)
