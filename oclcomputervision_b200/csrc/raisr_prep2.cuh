@@ -67,7 +67,9 @@ constexpr int P2_D = PH_H / 2;     // 32: phases 1-2 pair tile rows r and r + 32
 constexpr int P2_NU = PU_H - P2_D; // 34 pair rows of U: (n, n + 32), n = 0..33 (rows 32, 33 appear twice)
 constexpr int P2_UPITCH = 74;      // p2 per pair row: 37 x 16 B, odd -> 8 consecutive rows hit 8 bank groups
 
-constexpr int P2W_H = PW_H + 2, P2W_W = PW_W + 2, P2W_PITCH = P2W_W + 1;   // source window incl. the bicubic ring
+// source window incl. the bicubic ring and up to 3 columns of slack for a 4-byte aligned start; rows of 48 floats
+constexpr int P2W_H = PW_H + 2, P2W_W = PW_W + 2 + 3, P2W_PITCH = 48;
+static_assert(P2W_W <= P2W_PITCH && P2W_PITCH % 4 == 0, "window rows hold the aligned window and take 16-byte stores");
 
 // Tables of the bicubic stage-1 variant; they live in the first H plane, which is idle until phase 2.
 struct CubicTabs {
@@ -156,7 +158,11 @@ __global__ void __launch_bounds__(PT_THREADS, 3) prep2_kernel(const PrepParams p
     }
     __syncthreads();
     // ---- phase 0b: make the tables window-relative (x0/y0 are monotone, so first/last bound them)
-    const int wx0 = CUBIC ? ct.colx[0].x : sm.colx[0].x, wy0 = CUBIC ? ct.rowy[0].x : sm.rowy[0].x;
+    // With 4-byte aligned source rows the window starts on a word boundary and is fetched with 32-bit loads (four
+    // texels each, SURVEY.md 8(a7): no per-byte global loads); otherwise byte by byte.
+    const uint8_t* src = p.src + (size_t)frame * p.src_frame_stride;
+    const bool words = ((reinterpret_cast<uintptr_t>(src) | p.src_pitch) & 3) == 0;
+    const int wx0 = (CUBIC ? ct.colx[0].x : sm.colx[0].x) & (words ? ~3 : ~0), wy0 = CUBIC ? ct.rowy[0].x : sm.rowy[0].x;
     const int ww = (CUBIC ? ct.colx[PU_W - 1].w : sm.colx[PU_W - 1].y) - wx0 + 1;
     const int wh = (CUBIC ? ct.rowy[PU_H - 1].w : sm.rowy[PU_H - 1].y) - wy0 + 1;
     __syncthreads();
@@ -174,8 +180,17 @@ __global__ void __launch_bounds__(PT_THREADS, 3) prep2_kernel(const PrepParams p
         }
     }
     // ---- phase 0c: source window -> float texels (read_imagef UNORM8 decode), one LUT hit per texel
-    const uint8_t* src = p.src + (size_t)frame * p.src_frame_stride;
-    {   // 64 threads per window row (ww <= P2W_W = 42 of them active), four rows per pass: no index division
+    if (words) {   // 16 words per window row (<= 12 of them active), sixteen rows per pass
+        const int c4 = tid & 15;
+        if (4 * c4 < ww) {
+            const uint8_t* sp = src + (size_t)(wy0 + (tid >> 4)) * p.src_pitch + wx0 + 4 * c4;
+            float* wp = &sm.win[(tid >> 4) * P2W_PITCH + 4 * c4];
+            for (int r = tid >> 4; r < wh; r += 16, sp += 16 * p.src_pitch, wp += 16 * P2W_PITCH) {
+                const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(sp));
+                *reinterpret_cast<float4*>(wp) = make_float4(sm.lut[w & 0xffu], sm.lut[(w >> 8) & 0xffu], sm.lut[(w >> 16) & 0xffu], sm.lut[w >> 24]);
+            }
+        }
+    } else {       // 64 threads per window row, four rows per pass: no index division
         const int c = tid & 63;
         if (c < ww) {
             const uint8_t* sp = src + (size_t)(wy0 + (tid >> 6)) * p.src_pitch + wx0 + c;
