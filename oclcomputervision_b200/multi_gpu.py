@@ -96,7 +96,8 @@ class BandedUpscaler:
         D2H of the band (optional)                                              raisr_copy2d
 
     Before call k+1 overwrites the owned rows it waits for the neighbours' ``done`` >= k.  Device time is taken with
-    CUDA events on the same stream (``last_ms``).  The coordinate map uses the GLOBAL image size (raisr.cl:209).
+    CUDA events on the same stream (``last_ms``).  Every rank must make the same sequence of calls, and ``close()`` may
+    only be called once all ranks have finished their last call (it frees memory the neighbours have mapped).  The coordinate map uses the GLOBAL image size (raisr.cl:209).
     """
 
     FLAG_BYTES = 256          # [0] ready, [1] done; the rows start behind them
@@ -212,6 +213,9 @@ class BandedUpscaler:
 
     def close(self):
         if getattr(self, "base", None):
+            # The neighbours read their halo rows out of MY window and I poll words in THEIRS: the caller must make sure
+            # that every rank has finished its last call before any rank closes (a barrier or any collective; bench.py's
+            # all_reduce of the timings, the tests' barrier).
             try:
                 self.raisr.sync()
             except Exception:
