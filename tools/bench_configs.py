@@ -59,6 +59,7 @@ def main():
         F = synth.random_filters(s)
         r = ClRaisr(1)
         setattr(r, "filters_x%d" % s, F)
+        tap_format, b24_bound = r.effective_filters(s)[1:]
         host = make_frames(cfg)
         src = torch.from_numpy(host).cuda()
         dst = torch.empty((n, dh, dw), dtype=torch.uint8, device="cuda")
@@ -90,10 +91,11 @@ def main():
                    nominal_frames=cfg.get("nominal_frames", n), gpu_ms=round(ms, 3), gpu_mpix_s=round(gpu_mpix_s, 1),
                    prep_ms=round(prep_ms, 3), filter_ms=round(filt_ms, 3),
                    ffma_roofline_frac=round(412.0 * mpix * 1e6 / (ms * 1e-3) / 74.45e12, 4),
-                   one_frame_h2d_kernel_d2h_ms=[round(x, 3) for x in one_ms])
+                   one_frame_h2d_kernel_d2h_ms=[round(x, 3) for x in one_ms], taps=tap_format, b24_bound=b24_bound)
         if not args.no_check:
             t0 = time.perf_counter()
-            ref = O.raisr_ref_c(host[0], F, s, nthreads=threads, want=("hash", "out_u8"))
+            small = dw * dh <= 64e6      # the dense float planes of the classification fit comfortably
+            ref = O.raisr_ref_c(host[0], F, s, nthreads=threads, want=("hash", "out_u8", "angle", "L1", "coherence") if small else ("hash", "out_u8"))
             one = time.perf_counter() - t0
             k = int(max(0, min(7, args.cpu_seconds / max(one, 1e-3) - 1)))
             t0 = time.perf_counter()
@@ -106,9 +108,15 @@ def main():
             d = np.abs(got.astype(np.int16) - ref["out_u8"].astype(np.int16))
             if h is not None:
                 same = h == ref["hash"]
-                res.update(hash_mismatch=int((~same).sum()), out_u8_max_diff_where_hash_equal=int(d[same].max()))
+                excused = (~same) & (O.edge_distance(ref) < 1e-5)      # oracle value within 1e-5 of a bin edge (north_star)
+                res.update(hash_mismatch=int((~same).sum()), hash_mismatch_excused=int(excused.sum()),
+                           hash_mismatch_unexcused=int(((~same) & ~excused).sum()),
+                           out_u8_max_diff_where_hash_equal=int(d[same].max()))
             else:   # image too large for the dense int32/float debug planes: bound the pixels that may differ
-                res.update(pixels_over_1lsb=int((d > 1).sum()), pixels=int(d.size))
+                res.update(pixels_over_1lsb=int((d > 1).sum()), pixels=int(d.size),
+                           note="the per-pixel classification needs 40 GB of float planes at this size; the same x3 kernels are "
+                                "classified in full at 4128x4200 by tests/test_configs_gpu.py (6 excused, 0 unexcused of 17.3 M), "
+                                "i.e. ~3.5e-7 of the pixels sit on a bin edge: ~840 expected here")
             res.update(cpu_oracle_mpix_s=round(cpu_mpix_s, 2), cpu_threads=threads, cpu_frames=k + 1,
                        speedup_vs_cpu_oracle=round(gpu_mpix_s / cpu_mpix_s, 1))
         line = json.dumps(res)
