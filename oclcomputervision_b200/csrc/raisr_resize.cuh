@@ -331,4 +331,115 @@ __global__ void __launch_bounds__(kFastThreads) resize_bilinear_gray_kernel(cons
     }
 }
 
+// ---- the same recipe for interleaved 4-channel (BGRA) images, the format the reference's clUtility works on
+// (interpolation.py:43,61,79,97): one thread = one output column (one 32-bit store per row, 128 contiguous bytes per
+// warp), its two window offsets and x weights in registers for all rows of the tile, texels decoded once into a
+// float4 window, vertical texel reuse, the products of channel pairs (B,G) and (R,A) as packed FMUL2.
+constexpr int kFast4Cols = 128, kFast4Rows = 32, kFast4Threads = 128;
+
+inline long long resize_fast4_win_floats(const ResizeParams& p)
+{
+    const long long ww = (long long)kFast4Cols * p.sw / p.dw + 4, wh = (long long)kFast4Rows * p.sh / p.dh + 5;
+    return 4 * ww * wh;
+}
+
+inline bool resize_fast4_ok(const ResizeParams& p)
+{
+    if (p.channels != 4 || p.mode == 1) return false;
+    if (((reinterpret_cast<uintptr_t>(p.src) | p.src_pitch | p.src_frame_stride | reinterpret_cast<uintptr_t>(p.dst) | p.dst_pitch | p.dst_frame_stride) & 3) != 0) return false;
+    return resize_fast4_win_floats(p) <= kFastWin;
+}
+
+__global__ void __launch_bounds__(kFast4Threads) resize_bilinear_bgra_kernel(const ResizeParams p)
+{
+    extern __shared__ __align__(16) float win[];               // resize_fast4_win_floats(p) floats: [row][column] float4
+    __shared__ float lut[256];
+    __shared__ __align__(16) FastRow rowt[kFast4Rows];
+    __shared__ int wbox[4];
+    const int tid = threadIdx.x;
+    const int x = blockIdx.x * kFast4Cols + tid, y0 = blockIdx.y * kFast4Rows;
+    const int rows = min(kFast4Rows, p.dh - y0);
+    lut[tid] = __fdiv_rn((float)tid, 255.0f);
+    lut[tid + 128] = __fdiv_rn((float)(tid + 128), 255.0f);
+    auto map = [&](int i, int nd, int ns) {
+        return p.mode == 2 ? __fsub_rn(__fmul_rn(__fdiv_rn((float)i, (float)(nd - 1)), (float)ns), 0.5f)
+                           : __fmul_rn(__fdiv_rn((float)i, (float)(nd - 1)), (float)(ns - 1));
+    };
+    int ya_abs = 0, yb_abs = 0;
+    float vrow = 0.0f;
+    if (tid < kFast4Rows) {
+        const float fy = map(min(y0 + tid, p.dh - 1), p.dh, p.sh);
+        const float fl = floorf(fy);
+        ya_abs = min(max((int)fl, 0), p.sh - 1); yb_abs = min(max((int)fl + 1, 0), p.sh - 1);
+        vrow = __fsub_rn(fy, fl);
+        if (tid == 0) wbox[2] = ya_abs;
+        if (tid == rows - 1) wbox[3] = yb_abs;
+    }
+    const float fx = map(min(x, p.dw - 1), p.dw, p.sw);
+    const float flx = floorf(fx);
+    const int xa = min(max((int)flx, 0), p.sw - 1), xb = min(max((int)flx + 1, 0), p.sw - 1);
+    const float u = __fsub_rn(fx, flx), omu = __fsub_rn(1.0f, u);
+    if (tid == 0) wbox[0] = xa;
+    if (tid == kFast4Threads - 1) wbox[1] = xb;
+    __syncthreads();
+    const int wx0 = wbox[0], ww = wbox[1] - wx0 + 1;
+    const int wy0 = wbox[2], wh = wbox[3] - wy0 + 1;
+    if (tid < kFast4Rows) rowt[tid] = FastRow{(ya_abs - wy0) * ww * 16, (yb_abs - wy0) * ww * 16, __fsub_rn(1.0f, vrow), vrow};
+    const uint8_t* src = p.src + (size_t)blockIdx.z * p.src_frame_stride + (size_t)wy0 * p.src_pitch + (size_t)wx0 * 4;
+    for (int r = 0; r < wh; r += 4) {                          // four rows per pass: their loads are in flight together
+        for (int c = tid; c < ww; c += kFast4Threads) {
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                w[k] = (r + k < wh) ? __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)(r + k) * p.src_pitch) + c) : 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (r + k < wh)
+                    *reinterpret_cast<float4*>(&win[4 * ((r + k) * ww + c)]) =
+                        make_float4(lut[w[k] & 0xffu], lut[(w[k] >> 8) & 0xffu], lut[(w[k] >> 16) & 0xffu], lut[w[k] >> 24]);
+        }
+    }
+    __syncthreads();
+    if (x >= p.dw) return;
+    const int oa = 16 * (xa - wx0), ob = 16 * (xb - wx0);
+    const p2 OMU = bc(omu), U = bc(u);
+    uint8_t* drow = p.dst + (size_t)blockIdx.z * p.dst_frame_stride + (size_t)y0 * p.dst_pitch + (size_t)x * 4;
+    const char* wbase = reinterpret_cast<const char*>(win);
+    auto W4 = [&](int off, p2& bg, p2& ra) {
+        const float4 f = *reinterpret_cast<const float4*>(wbase + off);
+        bg = pk(f.x, f.y); ra = pk(f.z, f.w);
+    };
+    p2 ta_bg = 0, ta_ra = 0, tb_bg = 0, tb_ra = 0, ba_bg = 0, ba_ra = 0, bb_bg = 0, bb_ra = 0;   // upper / lower row, taps a / b
+    int cur_ya = -1, cur_yb = -1;
+    for (int r = 0; r < rows; ++r) {
+        const FastRow rt = rowt[r];
+        if (rt.ya != cur_ya || rt.yb != cur_yb) {              // the row table is CTA-uniform: uniform branches
+            if (rt.ya == cur_yb) { ta_bg = ba_bg; ta_ra = ba_ra; tb_bg = bb_bg; tb_ra = bb_ra; }
+            else if (rt.ya != cur_ya) { W4(rt.ya + oa, ta_bg, ta_ra); W4(rt.ya + ob, tb_bg, tb_ra); }
+            if (rt.yb == rt.ya) { ba_bg = ta_bg; ba_ra = ta_ra; bb_bg = tb_bg; bb_ra = tb_ra; }
+            else { W4(rt.yb + oa, ba_bg, ba_ra); W4(rt.yb + ob, bb_bg, bb_ra); }
+            cur_ya = rt.ya; cur_yb = rt.yb;
+        }
+        const p2 OMV = bc(rt.omv), V = bc(rt.v);
+        const p2 w00 = mul2(OMU, OMV), w01 = mul2(U, OMV), w10 = mul2(OMU, V), w11 = mul2(U, V);   // both halves equal
+        float q[4];
+        auto blend = [&](p2 ta, p2 tb, p2 ba, p2 bb, float& o0, float& o1) {
+            float l0, h0, l1, h1;
+            upk(mul2(w00, ta), l0, h0);
+            upk(mul2(w01, tb), l1, h1);
+            float a0 = __fadd_rn(l0, l1), a1 = __fadd_rn(h0, h1);
+            upk(mul2(w10, ba), l0, h0);
+            a0 = __fadd_rn(a0, l0); a1 = __fadd_rn(a1, h0);
+            upk(mul2(w11, bb), l0, h0);
+            o0 = __fadd_rn(a0, l0); o1 = __fadd_rn(a1, h0);
+        };
+        blend(ta_bg, tb_bg, ba_bg, bb_bg, q[0], q[1]);
+        blend(ta_ra, tb_ra, ba_ra, bb_ra, q[2], q[3]);
+        // write_imagef to UNORM_INT8 (a bilinear blend of [0,1] texels needs no explicit clamp, see the gray kernel)
+        const unsigned b0 = __float2uint_rn(__fmul_rn(q[0], 255.0f)), b1 = __float2uint_rn(__fmul_rn(q[1], 255.0f));
+        const unsigned b2 = __float2uint_rn(__fmul_rn(q[2], 255.0f)), b3 = __float2uint_rn(__fmul_rn(q[3], 255.0f));
+        *reinterpret_cast<uint32_t*>(drow + (size_t)r * p.dst_pitch) = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+    }
+}
+
 }  // namespace raisr

@@ -82,25 +82,30 @@ def test_gpu_reference_demo_shapes_and_psnr():
                                        ((50, 77), (45, 61)), ((300, 700), (301, 1203)), ((9, 16), (36, 64)), ((1, 8), (2, 16)),
                                        ((120, 2000), (130, 2100)), ((700, 64), (90, 40))])
 @pytest.mark.parametrize("mode", ["bilinear_lds", "bilinear"])
-def test_gpu_fast_gray_bilinear_kernel_bit_exact(shape, out, mode):
-    """The four-pixels-per-thread gray kernel (csrc/raisr_resize.cuh, the default for aligned gray bilinear resizes
-    and for ClRaisr.bilinear_only = the shipped raisr kernel's output) against the oracle and against the generic
+@pytest.mark.parametrize("ch", [1, 4])
+def test_gpu_fast_gray_bilinear_kernel_bit_exact(shape, out, mode, ch):
+    """The fast bilinear kernels (csrc/raisr_resize.cuh: four pixels per thread for gray -- also ClRaisr.bilinear_only,
+    the shipped raisr kernel's output -- and one BGRA pixel per thread) against the oracle and against the generic
     kernel, on up-scales, down-scales, ragged widths (stores of 1-3 leftover bytes) and tiles whose window is larger
     than the fast path allows (falls back)."""
     import ctypes
     from oclcomputervision_b200 import _cabi
     from oclcomputervision_b200.interpolation import clUtility
     rng = np.random.default_rng(out[1])
-    src = rng.integers(0, 256, shape, dtype=np.uint8)
+    src = rng.integers(0, 256, shape + ((4,) if ch == 4 else ()), dtype=np.uint8)
     want = O.resize_u8_c(src, out, mode)
     util = clUtility()
     lib = _cabi.load()
     res = []
     for fast in (1, 0):
         _cabi.check(lib.raisr_set_option(util._h, b"resize_fast", fast))
-        pitch = (out[1] + 3) // 4 * 4                      # 4-byte aligned rows qualify for the fast kernel
-        canvas = np.full((out[0] + 1, pitch + 4), 173, np.uint8)
-        dst = canvas[:out[0], :out[1]]
+        pitch = (out[1] + 3) // 4 * 4                      # 4-byte aligned rows qualify for the fast kernels
+        if ch == 4:
+            canvas = np.full((out[0] + 1, out[1] + 2, 4), 173, np.uint8)
+            dst = canvas[:out[0], :out[1]]
+        else:
+            canvas = np.full((out[0] + 1, pitch + 4), 173, np.uint8)
+            dst = canvas[:out[0], :out[1]]
         getattr(util, mode)(src, dst)
         assert np.array_equal(dst, want), (mode, fast)
         assert (canvas[:, out[1]:] == 173).all() and (canvas[-1] == 173).all()      # nothing written beyond the image
