@@ -386,6 +386,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the variants / band / next_rows sub-records")
     ap.add_argument("--filter-impl", type=int, default=None, help="1 octet (default), 0 block")
     ap.add_argument("--prep-ctas", type=int, default=None, help="persistent prep grid: CTAs per SM (0 = one CTA per tile)")
+    ap.add_argument("--eig", type=int, default=None, help="1: eigen-solve / hash inside the filter kernel (s = 2, b24)")
     ap.add_argument("--duo", type=int, default=None, help="1: two pixel types per CTA for s = 2 with b24 records, 0: one type per CTA")
     ap.add_argument("--overlap", type=int, default=None, help="1: overlapped prep/filter pipeline, 0: serial")
     ap.add_argument("--taps", default="auto", choices=["auto", "fp32", "fp16", "b24"],
@@ -419,6 +420,8 @@ def main():
         r.set_option("overlap", args.overlap)
     if args.duo is not None:
         r.set_option("filter_duo", args.duo)
+    if args.eig is not None:
+        r.set_option("eigen_in_filter", args.eig)
     if args.prep_ctas is not None:
         r.set_option("prep_ctas_per_sm", args.prep_ctas)
     if args.chunk_mb is not None:

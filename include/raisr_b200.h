@@ -79,6 +79,10 @@ int raisr_set_quantizers(raisr_t* h, const float* strength_q, int n_sq, const fl
  * the handle's own stream).  Stands in for the reference's CommandQueue (raisr.py:72). */
 int raisr_set_stream(raisr_t* h, void* cuda_stream);
 
+/* (further tuning keys, results unchanged: "filter_duo" 1 = both pixel types of an output row per CTA for s = 2 with
+ * 24-bit records (default), 0 = one type per CTA; "eigen_in_filter" 1 = the prep kernel stores the structure tensor and
+ * the s = 2 filter kernel does the eigen-solve / hash (default 0: measured slower); "resize_fast" 0 = generic resize
+ * kernel only; "prep_ctas_per_sm" n > 0 = persistent prep grid (default 0).) */
 /* Tuning knobs without a reference counterpart.  Keys: "filter_impl" (1 = octet kernel, default;
  * 0 = block kernel), "chunk_budget_bytes" (size of the per-launch upscaled-image scratch, default 208 MiB),
  * "overlap" (1 = experimental two-stream pipeline that co-schedules the prep kernel of the next chunk

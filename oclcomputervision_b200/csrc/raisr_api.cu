@@ -207,9 +207,21 @@ int enqueue_frames(raisr_ctx* h, const uint8_t* dsrc, int sw, int sh, size_t src
         h->scratch_release(st);
         return -1000 - nchunks;   // overlapped: caller reads the event layout above
     }
+    // eigen_in_filter: s = 2, 24-bit records, the reference's 3 x 3 quantisers, octet kernel with the tile pipeline
+    const bool eig = h->eig && scale == 2 && h->filter_impl == 1 && h->filter_pipe && h->tables[2].format == kTapsB24 &&
+                     h->n_strength <= 3 && h->n_coherence <= 3 && h->prep_impl == 2 && !h->cubic;
+    const size_t tens_plane = g.hash_frame * (size_t)chunk;   // elements per tensor plane
+    if (eig)
+        if (int rc = h->tens.ensure(3 * tens_plane * sizeof(float))) return rc;
     for (int f0 = 0; f0 < nf; f0 += chunk) {
         int n = std::min(chunk, nf - f0);
         fill_params(h, g, dsrc, sw, sh, src_pitch, ddst, dst_pitch, scale, f0, n, (float*)h->uext.p, (uint8_t*)h->hash.p, pp, fp);
+        if (eig) {
+            pp.tens = (float*)h->tens.p; pp.tens_plane_stride = tens_plane;
+            fp.tens = (const float*)h->tens.p; fp.tens_plane_stride = tens_plane;
+            fp.sq[0] = h->sq[0]; fp.sq[1] = h->sq[1]; fp.cq[0] = h->cq[0]; fp.cq[1] = h->cq[1];
+            fp.n_angle = h->n_angle; fp.n_strength = h->n_strength; fp.n_coherence = h->n_coherence; fp.as_written = h->as_written;
+        }
         size_t e = ev_base + 3 * (size_t)(f0 / chunk);
         if (timed) cudaEventRecord(h->ev(e), st);
         if (int rc = launch_prep(h, pp, scale, st, false, h->prep_ctas_per_sm)) return rc;
@@ -435,7 +447,7 @@ void raisr_destroy(raisr_t* h)
     Guard guard(h->device);
     cudaDeviceSynchronize();
     for (auto& t : h->tables) { t.block.release(); t.octet.release(); t.octet16.release(); t.b24.release(); }
-    h->uext.release(); h->hash.release(); h->dbg.release(); h->uext2.release(); h->hash2.release(); h->cplanes.release();
+    h->uext.release(); h->hash.release(); h->dbg.release(); h->uext2.release(); h->hash2.release(); h->cplanes.release(); h->tens.release();
     if (h->prep_stream) cudaStreamDestroy(h->prep_stream);
     if (h->filt_stream) cudaStreamDestroy(h->filt_stream);
     for (int b = 0; b < 2; ++b) { h->dsrc[b].release(); h->ddst[b].release(); }
@@ -591,6 +603,7 @@ int raisr_set_option(raisr_t* h, const char* key, long long value)
     }
     if (!strcmp(key, "prep_impl")) { h->prep_impl = value == 1 ? 1 : 2; return 0; }
     if (!strcmp(key, "prep_ctas_per_sm")) { h->prep_ctas_per_sm = (int)std::max<long long>(0, std::min<long long>(value, 8)); return 0; }
+    if (!strcmp(key, "eigen_in_filter")) { h->eig = value ? 1 : 0; return 0; }
     if (!strcmp(key, "filter_duo")) { h->duo = value ? 1 : 0; return 0; }
     if (!strcmp(key, "resize_fast")) { h->resize_fast = value ? 1 : 0; return 0; }
     if (!strcmp(key, "filter_pipe")) { h->filter_pipe = value ? 1 : 0; return 0; }

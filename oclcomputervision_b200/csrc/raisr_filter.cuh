@@ -40,6 +40,12 @@ struct FilterParams {
     int n_frames;
     int tiles_x, tiles_y;
     int raw_f32;              // float output is stored unclamped (colour path: CSC back happens before saturation)
+    // "eigen_in_filter": the filter kernel reads the structure tensor (three float planes, geometry of the hash image,
+    // see PrepParams::tens) and does the eigen-solve / hash itself
+    const float* tens;
+    size_t tens_plane_stride;
+    float sq[2], cq[2];
+    int n_angle, n_strength, n_coherence, as_written;
 };
 
 template <int S, int OTW, int OTH, int BR, int BC>

@@ -81,6 +81,7 @@ struct raisr_ctx {
     DevBuf uext, hash, dsrc[2], ddst[2], dbg;
     DevBuf uext2, hash2;          // second scratch set of the overlapped pipeline
     DevBuf cplanes;               // colour path: four filtered float planes
+    DevBuf tens;                  // eigen_in_filter: three float planes (ma, mb, md) with the geometry of the hash image
     cudaStream_t prep_stream = nullptr, filt_stream = nullptr;
     int overlap = 0;              // 1: prep of chunk c+1 shares the SMs with the filter of chunk c
     std::vector<cudaEvent_t> ev_pool;
@@ -110,6 +111,7 @@ struct raisr_ctx {
     int filter_pipe = 1;        // 1 = mbarrier full/empty tile pipeline with a producer warp (default), 0 = CTA-wide barriers per tile
     int color_filter_impl = 2;  // 2 = two planes per CTA (s = 2, fp32 taps), 1 = one launch per plane
     int prep_ctas_per_sm = 0;   // 0 = one prep CTA per tile (default), n > 0 = persistent grid of n CTAs per SM striding over the tiles
+    int eig = 0;          // "eigen_in_filter": 1 = prep stores the structure tensor and the s = 2 b24 filter kernel does the eigen-solve / hash
     int duo = 1;          // "filter_duo": 1 = two pixel types per CTA for s = 2 with b24 records (default), 0 = one type per CTA
     int resize_fast = 1;  // 1 = four-pixels-per-thread kernel for gray bilinear resizes that qualify (default), 0 = generic kernel
     int cubic = 0;        // "cheap_upscaler" option: 1 = bicubic stage 1 (gray path, prep2 kernel)

@@ -25,6 +25,7 @@
 
 #include "packed_f32.cuh"
 #include "raisr_filter.cuh"
+#include "raisr_prep.cuh"     // eigen_bucket() for the EIG variant
 
 namespace raisr {
 
@@ -284,7 +285,7 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar)
 // Producer side of the pipelined kernel: one thread fills a tile buffer with two TMA boxes -- the U tile
 // (as below) and the tile's hash bytes (OTW x OTH box of the planar hash image; rows past the image are
 // zero-filled) -- both signalled on the buffer's "full" mbarrier.
-template <int S>
+template <int S, bool WITH_HASH = true>
 __device__ __forceinline__ void octet_issue_tile_tma(const CUtensorMap* tm, const CUtensorMap* hm, unsigned char* buf, unsigned bar,
                                                      const TileCursor& tc, int type, int py, int px)
 {
@@ -292,12 +293,13 @@ __device__ __forceinline__ void octet_issue_tile_tma(const CUtensorMap* tm, cons
     using G = OctetGeom<S>;
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(buf);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx(bar, G::TILE_BYTES + G::HASH_BYTES);
+    mbar_expect_tx(bar, G::TILE_BYTES + (WITH_HASH ? G::HASH_BYTES : 0));
     const int r0 = (S * tc.ty * C::OTH + py) & ~3, c0 = S * tc.tx * C::OTW + px;
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  ::"r"(sbase), "l"(tm), "r"(r0), "r"(c0), "r"(tc.frame), "r"(bar) : "memory");
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-                 ::"r"(sbase + G::HASH_OFF), "l"(hm), "r"(tc.tx * C::OTW), "r"(tc.ty * C::OTH), "r"(type), "r"(tc.frame), "r"(bar) : "memory");
+    if (WITH_HASH)
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                     ::"r"(sbase + G::HASH_OFF), "l"(hm), "r"(tc.tx * C::OTW), "r"(tc.ty * C::OTH), "r"(type), "r"(tc.frame), "r"(bar) : "memory");
 }
 
 // Asynchronous fill of one tile buffer.  The U tile (rows S*oy0+py .., columns S*ox0+px .. of the
@@ -340,11 +342,18 @@ __device__ __forceinline__ void octet_issue_tile(const FilterParams& p, const CU
 // longer drains at every tile boundary (filter 11.04 -> 10.4 ms per step).
 // TF = kTapsB24: 384-byte records of 24-bit taps (see octet_pack_filter_b24): three predicated LDS.128 per lane and
 // pixel instead of four, twelve PRMT on the otherwise idle integer pipe, the same fp32 FMA chain.
-template <int S, typename OutT, int NBUF = 2, int TF = kTapsF32, bool PIPE = false>
+// EIG (PIPE, b24 only): "eigen in the filter kernel".  prep2_kernel stops after the structure tensor and stores
+// ma, mb, md; here lane q of an octet solves the eigen problem of pixel b0 + q of every batch of eight (the scalar
+// sequence eigen_bucket(), bit-identical to the prep kernels), and three shuffles pack the eight buckets into the two
+// words the pixel loop reads its hash bytes from.  The eigen-solve is 52 % of the prep kernel's instructions, and the
+// packed-FFMA2 filter kernel is bound by shared memory with a third of its issue slots idle: the work moves from an
+// issue-bound kernel into the issue shadow of a memory-bound one.
+template <int S, typename OutT, int NBUF = 2, int TF = kTapsF32, bool PIPE = false, bool EIG = false>
 __global__ void __launch_bounds__(OctetCfg<S>::NT, 1)
     filter_octet_kernel(const FilterParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap hmap)
 {
     static_assert(!PIPE || NBUF == 2, "the pipelined kernel is double-buffered");
+    static_assert(!EIG || (PIPE && TF == kTapsB24), "the eigen-in-filter variant is built for the pipelined b24 kernel");
     using C = OctetCfg<S>;
     using G = OctetGeom<S>;
     constexpr bool H16 = TF == kTapsF16, B24 = TF == kTapsB24;
@@ -386,7 +395,7 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1)
         TileCursor pc = cur;
         int pit = 0;
         for (int tile = worker; tile < ntiles && pit < 2; tile += nworkers, ++pit) {
-            octet_issue_tile_tma<S>(&tmap, &hmap, pit ? buf1 : buf0, pit ? bar1 : bar0, pc, type, py, px);
+            octet_issue_tile_tma<S, !EIG>(&tmap, &hmap, pit ? buf1 : buf0, pit ? bar1 : bar0, pc, type, py, px);
             pc.advance(nworkers, p.tiles_x, p.tiles_y);
         }
     }
@@ -441,6 +450,27 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1)
             const float* base = reinterpret_cast<const float*>(buf) + S * (seg * C::IW) * G::PT + S * row + (py & 3);   // S*OTH % 4 == 0
             const float* pf = base + off_full;
             const uint2* hrow = reinterpret_cast<const uint2*>(buf + G::HASH_OFF + row * C::OTW + seg * C::IW);
+            // EIG: structure tensor of "my" pixel (lane8) of the next two batches of eight, fetched ahead
+            const float* trow = nullptr;
+            float e0a = 0, e0b = 0, e0d = 0, e1a = 0, e1b = 0, e1d = 0;
+            auto tens_load = [&](int ox, float& a, float& b, float& d) {
+                const float* t = trow + min(ox, p.ow - 1);
+                a = __ldg(t); b = __ldg(t + p.tens_plane_stride); d = __ldg(t + 2 * p.tens_plane_stride);
+            };
+            auto eig_pack = [&](float a, float b, float d) {      // my pixel's bucket -> the eight hash bytes of the batch
+                const float sq[2] = {p.sq[0], p.sq[1]}, cq[2] = {p.cq[0], p.cq[1]};
+                const unsigned mine = (unsigned)eigen_bucket<2>(a, b, d, sq, cq, p.n_angle, p.n_strength, p.n_coherence, p.as_written != 0);
+                unsigned v = mine << (8 * (lane8 & 3));
+                v |= __shfl_xor_sync(omask, v, 1);
+                v |= __shfl_xor_sync(omask, v, 2);
+                const unsigned other = __shfl_xor_sync(omask, v, 4);
+                return (lane8 & 4) ? make_uint2(other, v) : make_uint2(v, other);
+            };
+            if (EIG) {
+                trow = p.tens + (size_t)cur.frame * p.hash_frame_stride + (size_t)type * p.hash_plane_stride + (size_t)oy * p.hash_pitch;
+                tens_load(oxs + lane8, e0a, e0b, e0d);
+                tens_load(oxs + 8 + lane8, e1a, e1b, e1d);
+            }
             // circular register windows: element j of pixel i lives in slot (S*i + j) % W
             float w11[G::WF], w5[G::WP];
 #pragma unroll
@@ -458,7 +488,7 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1)
             for (int t = 0; t < G::NEWP; ++t) w5[5 - G::NEWP + t] = base[off_part[t]];
             // hash bytes are always < n_buckets: the prep kernel writes valid buckets only and the host zero-fills the
             // scratch when it allocates it (padding bytes never hold anything else), so no clamp is needed here
-            uint2 hb = hrow[0];
+            uint2 hb = EIG ? eig_pack(e0a, e0b, e0d) : hrow[0];
             unsigned bucket = hb.x & 0xffu;
             const float4* tp = tab_lane + bucket * (REC / 16);
             float4 t0 = {}, t1 = {}, t2 = {}, t3 = {};
@@ -473,7 +503,16 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1)
 #pragma unroll 1
             for (int b0 = 0; b0 < C::IW; b0 += 8) {
                 if (oxs + b0 >= p.ow) break;                  // octet-uniform
-                const uint2 hnext = hrow[min(b0 / 8 + 1, C::IW / 8 - 1)];   // hash bytes of the next batch
+                uint2 hnext;                                  // hash bytes of the next batch
+                if (EIG) {
+                    hnext = make_uint2(0u, 0u);
+                    if (b0 + 8 < C::IW) {                         // uniform
+                        hnext = eig_pack(e1a, e1b, e1d);
+                        if (b0 + 16 < C::IW) tens_load(oxs + b0 + 16 + lane8, e1a, e1b, e1d);
+                    }
+                } else {
+                    hnext = hrow[min(b0 / 8 + 1, C::IW / 8 - 1)];
+                }
                 float acc[8];
 #pragma unroll
                 for (int b = 0; b < 8; ++b) {
@@ -599,7 +638,7 @@ __global__ void __launch_bounds__(OctetCfg<S>::NT, 1)
                     if (tile + 2 * nworkers < ntiles) {
                         TileCursor t2 = cur;                             // cur already points at the next tile
                         t2.advance(nworkers, p.tiles_x, p.tiles_y);
-                        octet_issue_tile_tma<S>(&tmap, &hmap, buf, (it & 1) ? bar1 : bar0, t2, type, py, px);
+                        octet_issue_tile_tma<S, !EIG>(&tmap, &hmap, buf, (it & 1) ? bar1 : bar0, t2, type, py, px);
                     }
                 }
             }

@@ -396,6 +396,17 @@ __global__ void __launch_bounds__(PT_THREADS, 3) prep2_kernel(const PrepParams p
             const p2 ma = p.as_written ? mb : *reinterpret_cast<const p2*>(hp);            // raisr.cl:271 accumulates gx*gy into ma
             const p2 md = *reinterpret_cast<const p2*>(hp + 2 * PH_H * PH_PITCH);
             hp += PH_PITCH;
+            if (!DBG && p.tens) {    // the filter kernel solves the eigen problem: hand it the tensor (uniform branch)
+                if (yl0 + j < p.rows) {
+                    float* t0 = p.tens + (hrow - p.hash);
+                    float al, ah, bl, bh, dl, dh;
+                    upk(ma, al, ah); upk(mb, bl, bh); upk(md, dl, dh);
+                    if (okl) { t0[offl] = al; t0[offl + p.tens_plane_stride] = bl; t0[offl + 2 * p.tens_plane_stride] = dl; }
+                    if (okh) { t0[offh] = ah; t0[offh + p.tens_plane_stride] = bh; t0[offh + 2 * p.tens_plane_stride] = dh; }
+                }
+                if (++yt == S) { yt = 0; hrow += wrap_step; } else hrow += row_step;
+                continue;
+            }
             const p2 T = add2(ma, md);
             float dal, dah, dbl, dbh;                       // scalar subtraction: see the note on contraction in phase 1
             upk(mul2(ma, md), dal, dah);

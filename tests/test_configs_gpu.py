@@ -297,3 +297,26 @@ def test_near_flat_frames_tiny_tensors_and_exact_zeros(raisr, s):
     assert ((T > 0) & (T < 5e-11)).any() and (T == 0).any() and (T > 1e-8).any()     # all three regimes are present
     res = check_against_oracle(raisr, src, s, F, 1, label="near-flat x%d: " % s)
     assert res["unexcused"] == 0
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (3, 200), (37, 53), (130, 67), (270, 480)])
+def test_eigen_in_filter_equals_two_kernel_split(shape):
+    """`eigen_in_filter` = 1: prep2_kernel stores the structure tensor and the s = 2 b24 filter kernel does the
+    eigen-solve / hash itself (eigen_bucket, the scalar sequence that is bit-identical to the packed one).  Outputs
+    are bit-identical to the default split, for single frames, ragged sizes and multi-chunk batches."""
+    flt = synth.random_filters(2, seed=19)
+    n = 4
+    frames = np.stack([synth.synthetic_frame(max(shape[0], 8), max(shape[1], 8), seed=500 + k)[:shape[0], :shape[1]] for k in range(n)]).copy()
+    outs = []
+    for eig in (1, 0):
+        r = ClRaisr(1, filters=flt, device=0)
+        r.set_option("eigen_in_filter", eig)
+        r.set_option("filter_duo", 0)
+        dst = np.empty((n, 2 * shape[0], 2 * shape[1]), np.uint8)
+        r.upsample_batch(frames, dst, 2)
+        dstf = np.empty((n, 2 * shape[0], 2 * shape[1]), np.float32)
+        r.upsample_batch(frames, dstf, 2)
+        outs.append((dst, dstf))
+        r.close()
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1])
