@@ -861,7 +861,10 @@ int raisr_resize_u8(raisr_t* h, const uint8_t* src, int sw, int sh, size_t src_p
     cudaEventRecord(h->ev(1), st);
     ResizeParams rp{dsrc, src_pitch, src_frame, ddst, dst_pitch, dst_frame, sw, sh, dw, dh, channels, mode};
     dim3 grid((dw + 255) / 256, (dh + kResizeRows - 1) / kResizeRows, n_frames);
-    if (channels == 4 && resize_fast4_ok(rp) && h->resize_fast) {
+    if (channels == 4 && resize_cubic4_ok(rp) && h->resize_fast) {
+        dim3 fgrid((dw + kFast4Cols - 1) / kFast4Cols, (dh + kFast4Rows - 1) / kFast4Rows, n_frames);
+        resize_bicubic_bgra_kernel<<<fgrid, kFast4Threads, (size_t)resize_cubic4_win_floats(rp) * sizeof(float), st>>>(rp);
+    } else if (channels == 4 && resize_fast4_ok(rp) && h->resize_fast) {
         dim3 fgrid((dw + kFast4Cols - 1) / kFast4Cols, (dh + kFast4Rows - 1) / kFast4Rows, n_frames);
         resize_bilinear_bgra_kernel<<<fgrid, kFast4Threads, (size_t)resize_fast4_win_floats(rp) * sizeof(float), st>>>(rp);
     } else if (channels == 4) resize_kernel<4><<<grid, 256, 0, st>>>(rp);

@@ -442,4 +442,140 @@ __global__ void __launch_bounds__(kFast4Threads) resize_bilinear_bgra_kernel(con
     }
 }
 
+// ---- bicubic (Catmull-Rom, interpolation.cl:79-211) for BGRA images: one thread = one output column.  The oracle's
+// expression is acc += (pix[i][j] * xw[j]) * yw[i], i (row) outer, j inner: the 16 products pix * xw of a column
+// depend on the source row only, so they are kept in registers (four row slots, slot = source row & 3) and re-used by
+// every output row that needs the row; a new source row costs 4 shared loads and 16 multiplies per column, an output
+// row 64 multiplies (as 32 packed FMUL2 over the channel pairs (B,G), (R,A)) and 64 additions in the oracle's order.
+// The row schedule (which source rows, their weights, which slot holds which tap) is the same for the whole CTA, so
+// the four orders in which the slots can be read are four copies of the blend behind a uniform switch.
+struct CubicRow { int y[4]; float w[4]; int base; int pad[3]; };   // window-relative byte offsets of the 4 rows, y weights, first (unclamped) source row
+
+inline long long resize_cubic4_win_floats(const ResizeParams& p)
+{
+    const long long ww = (long long)kFast4Cols * p.sw / p.dw + 7, wh = (long long)kFast4Rows * p.sh / p.dh + 8;
+    return 4 * ww * wh;
+}
+
+inline bool resize_cubic4_ok(const ResizeParams& p)
+{
+    if (p.channels != 4 || p.mode != 1) return false;
+    if (((reinterpret_cast<uintptr_t>(p.src) | p.src_pitch | p.src_frame_stride | reinterpret_cast<uintptr_t>(p.dst) | p.dst_pitch | p.dst_frame_stride) & 3) != 0) return false;
+    return resize_cubic4_win_floats(p) <= kFastWin;
+}
+
+__global__ void __launch_bounds__(kFast4Threads) resize_bicubic_bgra_kernel(const ResizeParams p)
+{
+    extern __shared__ __align__(16) float win[];
+    __shared__ float lut[256];
+    __shared__ __align__(16) CubicRow rowt[kFast4Rows];
+    __shared__ int wbox[4];
+    const int tid = threadIdx.x;
+    const int x = blockIdx.x * kFast4Cols + tid, y0 = blockIdx.y * kFast4Rows;
+    const int rows = min(kFast4Rows, p.dh - y0);
+    lut[tid] = __fdiv_rn((float)tid, 255.0f);
+    lut[tid + 128] = __fdiv_rn((float)(tid + 128), 255.0f);
+    int yabs[4] = {0, 0, 0, 0}, ybase = 0;
+    float yw[4] = {0, 0, 0, 0};
+    if (tid < kFast4Rows) {
+        const float fy = __fmul_rn(__fdiv_rn((float)min(y0 + tid, p.dh - 1), (float)(p.dh - 1)), (float)(p.sh - 1));
+        const float fl = floorf(fy);
+        ybase = (int)fl - 1;
+        cubic_weights(__fsub_rn(fy, fl), yw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) yabs[i] = min(max(ybase + i, 0), p.sh - 1);
+        if (tid == 0) wbox[2] = yabs[0];
+        if (tid == rows - 1) wbox[3] = yabs[3];
+    }
+    const float fx = __fmul_rn(__fdiv_rn((float)min(x, p.dw - 1), (float)(p.dw - 1)), (float)(p.sw - 1));
+    const float flx = floorf(fx);
+    float xw[4];
+    cubic_weights(__fsub_rn(fx, flx), xw);
+    int xs[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xs[j] = min(max((int)flx - 1 + j, 0), p.sw - 1);
+    if (tid == 0) wbox[0] = xs[0];
+    if (tid == kFast4Threads - 1) wbox[1] = xs[3];
+    __syncthreads();
+    const int wx0 = wbox[0], ww = wbox[1] - wx0 + 1;
+    const int wy0 = wbox[2], wh = wbox[3] - wy0 + 1;
+    if (tid < kFast4Rows) {
+        CubicRow cr;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { cr.y[i] = (yabs[i] - wy0) * ww * 16; cr.w[i] = yw[i]; }
+        cr.base = ybase;
+        rowt[tid] = cr;
+    }
+    const uint8_t* src = p.src + (size_t)blockIdx.z * p.src_frame_stride + (size_t)wy0 * p.src_pitch + (size_t)wx0 * 4;
+    for (int r = 0; r < wh; r += 4) {
+        for (int c = tid; c < ww; c += kFast4Threads) {
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                w[k] = (r + k < wh) ? __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)(r + k) * p.src_pitch) + c) : 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (r + k < wh)
+                    *reinterpret_cast<float4*>(&win[4 * ((r + k) * ww + c)]) =
+                        make_float4(lut[w[k] & 0xffu], lut[(w[k] >> 8) & 0xffu], lut[(w[k] >> 16) & 0xffu], lut[w[k] >> 24]);
+        }
+    }
+    __syncthreads();
+    if (x >= p.dw) return;
+    int xo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xo[j] = 16 * (xs[j] - wx0);
+    uint8_t* drow = p.dst + (size_t)blockIdx.z * p.dst_frame_stride + (size_t)y0 * p.dst_pitch + (size_t)x * 4;
+    const char* wbase = reinterpret_cast<const char*>(win);
+    // h[slot][j] = (pix * xw[j]) of source row `slot` (mod 4), as channel pairs (B,G) and (R,A)
+    p2 hbg[4][4], hra[4][4];
+    auto load_row = [&](int slot, int yoff) {
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4)
+            if (s4 == slot) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 f = *reinterpret_cast<const float4*>(wbase + yoff + xo[j]);
+                    hbg[s4][j] = mul2(pk(f.x, f.y), bc(xw[j]));
+                    hra[s4][j] = mul2(pk(f.z, f.w), bc(xw[j]));
+                }
+            }
+    };
+    int have_lo = 1 << 30, have_hi = -(1 << 30);    // unclamped source rows currently in the slots: [have_lo, have_hi]
+    for (int r = 0; r < rows; ++r) {
+        const CubicRow cr = rowt[r];
+        // bring rows cr.base .. cr.base + 3 into the slots (uniform control flow: the row table is per CTA)
+        for (int i = 0; i < 4; ++i) {
+            const int yr = cr.base + i;
+            if (yr < have_lo || yr > have_hi) load_row(yr & 3, cr.y[i]);
+        }
+        have_lo = cr.base; have_hi = cr.base + 3;
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};     // B, G, R, A
+        auto blend = [&](int s0) {                   // s0 = slot of tap row 0; rows follow in slots s0+1, s0+2, s0+3 (mod 4)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const p2 YW = bc(cr.w[i]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float b, g, rr, a;
+                    upk(mul2(hbg[(s0 + i) & 3][j], YW), b, g);
+                    upk(mul2(hra[(s0 + i) & 3][j], YW), rr, a);
+                    acc[0] = __fadd_rn(acc[0], b); acc[1] = __fadd_rn(acc[1], g);
+                    acc[2] = __fadd_rn(acc[2], rr); acc[3] = __fadd_rn(acc[3], a);
+                }
+            }
+        };
+        switch (cr.base & 3) {
+        case 0: blend(0); break;
+        case 1: blend(1); break;
+        case 2: blend(2); break;
+        default: blend(3); break;
+        }
+        unsigned q[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) q[c] = __float2uint_rn(__fmul_rn(fminf(fmaxf(acc[c], 0.0f), 1.0f), 255.0f));
+        *reinterpret_cast<uint32_t*>(drow + (size_t)r * p.dst_pitch) = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
+    }
+}
+
 }  // namespace raisr

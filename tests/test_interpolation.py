@@ -81,12 +81,11 @@ def test_gpu_reference_demo_shapes_and_psnr():
 @pytest.mark.parametrize("shape,out", [((270, 480), (540, 960)), ((100, 300), (200, 600)), ((64, 100), (192, 300)), ((37, 53), (74, 106)),
                                        ((50, 77), (45, 61)), ((300, 700), (301, 1203)), ((9, 16), (36, 64)), ((1, 8), (2, 16)),
                                        ((120, 2000), (130, 2100)), ((700, 64), (90, 40))])
-@pytest.mark.parametrize("mode", ["bilinear_lds", "bilinear"])
-@pytest.mark.parametrize("ch", [1, 4])
+@pytest.mark.parametrize("mode,ch", [("bilinear_lds", 1), ("bilinear", 1), ("bilinear_lds", 4), ("bilinear", 4), ("bicubic", 4)])
 def test_gpu_fast_gray_bilinear_kernel_bit_exact(shape, out, mode, ch):
-    """The fast bilinear kernels (csrc/raisr_resize.cuh: four pixels per thread for gray -- also ClRaisr.bilinear_only,
-    the shipped raisr kernel's output -- and one BGRA pixel per thread) against the oracle and against the generic
-    kernel, on up-scales, down-scales, ragged widths (stores of 1-3 leftover bytes) and tiles whose window is larger
+    """The fast resize kernels (csrc/raisr_resize.cuh: bilinear with four pixels per thread for gray -- also
+    ClRaisr.bilinear_only, the shipped raisr kernel's output --, bilinear and bicubic with one BGRA pixel per thread)
+    against the oracle and against the generic kernel, on up-scales, down-scales, ragged widths (stores of 1-3 leftover bytes) and tiles whose window is larger
     than the fast path allows (falls back)."""
     import ctypes
     from oclcomputervision_b200 import _cabi
