@@ -699,7 +699,7 @@ static int enqueue_bgra_frame(raisr_ctx* h, const Geometry& g, const uint8_t* ds
     cu.src = dsrc; cu.src_pitch = src_pitch;
     cu.sw = sw; cu.sh = sh; cu.dw = dw; cu.dh = dh; cu.pitch = g.uext_pitch; cu.cubic = h->cubic;
     for (int k = 0; k < 4; ++k) cu.plane[k] = (float*)h->uext.p + g.uext_frame * k;
-    dim3 gu((dw + 2 * kMargin + 255) / 256, (dh + 2 * kMargin + 3) / 4);
+    dim3 gu((dw + 2 * kMargin + 255) / 256, (dh + 2 * kMargin + kColorUpRows - 1) / kColorUpRows);
     color_upscale_kernel<<<gu, 256, 0, st>>>(cu);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -1093,7 +1093,7 @@ int raisr_debug_hash_bgra(raisr_t* h, const uint8_t* src, int sw, int sh, size_t
     cu.src = dsrc; cu.src_pitch = src_pitch;
     cu.sw = sw; cu.sh = sh; cu.dw = dw; cu.dh = dh; cu.pitch = g.uext_pitch; cu.cubic = h->cubic;
     for (int k = 0; k < 4; ++k) cu.plane[k] = (float*)h->uext.p + g.uext_frame * k;
-    dim3 gu((dw + 2 * kMargin + 255) / 256, (dh + 2 * kMargin + 3) / 4);
+    dim3 gu((dw + 2 * kMargin + 255) / 256, (dh + 2 * kMargin + kColorUpRows - 1) / kColorUpRows);
     color_upscale_kernel<<<gu, 256, 0, st>>>(cu);
     h->launches++;
     CUDA_TRY(cudaGetLastError());

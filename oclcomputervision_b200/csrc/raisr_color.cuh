@@ -41,7 +41,9 @@ __device__ __forceinline__ float dot4_rn(const float* m, float a, float b, float
     return acc;
 }
 
-// One thread = one extended column x four consecutive extended rows (one 16-byte store per plane).
+// One thread = one extended column x kColorUpRows consecutive extended rows: 32 contiguous bytes (a full sector) per
+// plane of the column-major uext.
+constexpr int kColorUpRows = 8;
 __global__ void __launch_bounds__(256) color_upscale_kernel(const ColorUpParams p)
 {
     // read_imagef's UNORM8 decode v / 255 (correctly rounded) from a 256-entry table: the bilinear branch decodes 16
@@ -50,7 +52,7 @@ __global__ void __launch_bounds__(256) color_upscale_kernel(const ColorUpParams 
     lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);
     __syncthreads();
     const int ec = blockIdx.x * blockDim.x + threadIdx.x;       // extended column
-    const int er0 = blockIdx.y * 4;                              // first extended row of the quad
+    const int er0 = blockIdx.y * kColorUpRows;                   // first extended row of the thread's run
     const int ew = p.dw + 2 * kMargin, eh = p.dh + 2 * kMargin;
     if (ec >= ew || er0 >= eh) return;
     const float fx = __fmul_rn(__fdiv_rn((float)(ec - kMargin), (float)(p.dw - 1)), (float)(p.sw - 1));
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(256) color_upscale_kernel(const ColorUpParams 
     const int xi = (int)flx;
     const float u = __fsub_rn(fx, flx), omu = __fsub_rn(1.0f, u);
     const int x0 = min(max(xi, 0), p.sw - 1), x1 = min(max(xi + 1, 0), p.sw - 1);
-    float out[4][4];
+    float out[4][kColorUpRows];
     if (p.cubic) {
         // cubic_sample (raisr.cl:63-106): 4x4 taps around floor(coord), w_k = dot((1,u,u2,u3), cubic_matrix[k]) left to
         // right, acc += (pix * xweight[j]) * yweight[i] with i outer / j inner, every channel clamped to [0,1]
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(256) color_upscale_kernel(const ColorUpParams 
 #pragma unroll
         for (int j = 0; j < 4; ++j) xs[j] = min(max(xi - 1 + j, 0), p.sw - 1);
 #pragma unroll 1
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < kColorUpRows; ++k) {
             const int er = er0 + k;
             const float fy = __fmul_rn(__fdiv_rn((float)(er - kMargin), (float)(p.dh - 1)), (float)(p.sh - 1));
             const float fly = floorf(fy);
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(256) color_upscale_kernel(const ColorUpParams 
         }
     } else
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < kColorUpRows; ++k) {
         const int er = er0 + k;
         const float fy = __fmul_rn(__fdiv_rn((float)(er - kMargin), (float)(p.dh - 1)), (float)(p.sh - 1));
         const float fly = floorf(fy);
@@ -129,7 +131,10 @@ __global__ void __launch_bounds__(256) color_upscale_kernel(const ColorUpParams 
     }
 #pragma unroll
     for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<float4*>(p.plane[c] + (size_t)ec * p.pitch + er0) = make_float4(out[c][0], out[c][1], out[c][2], out[c][3]);
+#pragma unroll
+        for (int q = 0; q < kColorUpRows / 4; ++q)      // the column pitch covers the rounded-up row count
+            *reinterpret_cast<float4*>(p.plane[c] + (size_t)ec * p.pitch + er0 + 4 * q) =
+                make_float4(out[c][4 * q], out[c][4 * q + 1], out[c][4 * q + 2], out[c][4 * q + 3]);
 }
 
 struct ColorPackParams {
