@@ -12,7 +12,8 @@
 #include "raisr_prep.cuh"     // PrepParams
 
 int raisr_fail(int code, const char* fmt, ...);   // records the thread-local message of raisr_last_error(), returns code
-#define fail raisr_fail
+template <typename... Args>
+inline int fail(int code, const char* fmt, Args... args) { return raisr_fail(code, fmt, args...); }
 
 #define CUDA_TRY(expr)                                                                         \
     do {                                                                                       \
