@@ -320,3 +320,36 @@ def test_eigen_in_filter_equals_two_kernel_split(shape):
         r.close()
     assert np.array_equal(outs[0][0], outs[1][0])
     assert np.array_equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("n_angle,n_strength,n_coherence,quirks", [(24, 3, 3, "as_written"), (8, 2, 2, "intended"), (28, 3, 3, "intended"),
+                                                                   (16, 4, 4, "intended")])
+def test_default_kernels_with_other_bucket_counts_and_quirks(n_angle, n_strength, n_coherence, quirks):
+    """The default s = 2 path (24-bit records, two-types-per-CTA kernel) with bucket counts other than 24x3x3 --
+    32 buckets; 252 buckets, where the two table slices no longer fit shared memory and the one-type kernel takes
+    over; 4 x 4 quantisers (general-quantiser prep instantiation) -- and with the as-written quirks."""
+    rng = np.random.default_rng(n_angle)
+    F = rng.normal(0, 0.02, (n_angle, n_strength, n_coherence, 4, 121))
+    F[..., 60] += 1
+    F = np.ascontiguousarray((F / F.sum(-1, keepdims=True)).astype(np.float32))
+    sq = [1e-4, 1e-3, 1e-2][:n_strength - 1]
+    cq = [0.25, 0.5, 0.75][:n_coherence - 1]
+    src = synth.synthetic_frame(140, 200, seed=77)
+    r = ClRaisr(1, filters=F, device=0, n_angle=n_angle, n_strength=n_strength, n_coherence=n_coherence, quirks=quirks)
+    r.set_quantizers(sq, cq)
+    ref = O.raisr_ref_c(src, F, 2, n_angle=n_angle, n_strength=n_strength, n_coherence=n_coherence, strength_q=sq, coherence_q=cq, quirks=quirks)
+    h = r.debug_hash(src, 2)[0]
+    bad = h != ref["hash"]
+    near = O.edge_distance(ref, n_angle=n_angle, strength_q=sq, coherence_q=cq, quirks=quirks) < EDGE_EPS
+    assert not (bad & ~near).any()
+    Feff, fmt, bound = r.effective_filters(2)
+    out = r.upsample_f32(src, 2)
+    assert np.abs(out - ref["out_f32"])[~bad].max() < TOL_F32
+    if fmt == "b24":
+        ref_eff = O.raisr_ref_c(src, Feff, 2, n_angle=n_angle, n_strength=n_strength, n_coherence=n_coherence, strength_q=sq, coherence_q=cq,
+                                quirks=quirks, want=("out_f32",))
+        assert np.abs(out - ref_eff["out_f32"])[~bad].max() < 5e-6
+    dst = np.empty((280, 400), np.uint8)
+    r.upsample(src, dst, 2)
+    assert np.abs(dst.astype(int) - ref["out_u8"].astype(int))[~bad].max() <= 1
+    r.close()
