@@ -1,0 +1,65 @@
+"""Generates tests/golden/ref_cl.npz: OUTPUTS OF THE REFERENCE'S OWN KERNEL (raisr.cl), run here on the CPU.
+
+    python oracle/make_golden_ref_cl.py          # build container only: needs /root/reference
+
+oracle/build_ref.py compiles the kernel source where it lies against oracle/ref_shim/cl_shim.hpp; this script runs it
+on small inputs the way ClRaisr.upsample does (oracle/raisr_cl_ref.py) and stores, per case, the source, the scale, the
+seed of the filter table (oclcomputervision_b200.synth.random_filters) and four destination images:
+
+    shipped_f16 / shipped_f32   the kernel as shipped (early return: bilinear only), `half` = binary16 / binary32
+    full_f16 / full_f32         the early return compiled out: the whole RAISR text runs
+
+These are the vectors that pin the oracle (tests/test_ref_pin.py) and, on the GPU box, the CUDA path directly
+(tests/test_ref_pin_gpu.py); /root/reference does not travel, the fixture does.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import raisr_cl_ref as R  # noqa: E402
+from oclcomputervision_b200 import synth  # noqa: E402
+
+VARIANTS = [(k, p) for k in ("shipped", "full") for p in ("f16", "f32")]
+
+
+def sources():
+    rng = np.random.default_rng(20260101)
+    lenna = np.load(os.path.join(ROOT, "tests", "golden", "lenna_x2.npz"))["src"]     # luma of /root/reference/images/lenna.png
+    step = np.full((24, 32), 30, np.uint8)
+    step[:, 16:] = 230
+    step[12:, :] = 255 - step[12:, :]
+    smooth3 = [synth.synthetic_frame(48, 64, seed=s) for s in (5, 6, 7)]
+    return {
+        "noise_x2": (rng.integers(0, 256, (40, 48), dtype=np.uint8), 2),
+        "smooth_x2": (synth.synthetic_frame(64, 80, seed=3), 2),
+        "lenna_x2": (np.ascontiguousarray(lenna[192:320, 192:320]), 2),
+        "smooth_x3": (synth.synthetic_frame(32, 48, seed=4), 3),
+        "smooth_x4": (synth.synthetic_frame(24, 28, seed=11), 4),
+        "flat_x2": (np.full((16, 24), 77, np.uint8), 2),
+        "step_x2": (step, 2),
+        "bgra_smooth_x2": (np.stack(smooth3 + [rng.integers(0, 256, (48, 64), dtype=np.uint8)], -1), 2),
+        "bgra_noise_x2": (rng.integers(0, 256, (32, 48, 4), dtype=np.uint8), 2),
+    }
+
+
+def main():
+    out = {}
+    for name, (src, s) in sources().items():
+        fseed = 100 + s
+        flt = synth.random_filters(s, seed=fseed)
+        out[name + "_src"] = src
+        out[name + "_scale"] = np.int32(s)
+        out[name + "_fseed"] = np.int32(fseed)
+        for kind, prec in VARIANTS:
+            out["%s_%s_%s" % (name, kind, prec)] = R.run(src, flt, s, kind=kind, prec=prec)
+        print(name, src.shape, "x%d" % s)
+    path = os.path.join(ROOT, "tests", "golden", "ref_cl.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,73 @@
+"""ctypes front end of oracle/_ref/libraisr_ref_*.so -- the reference's own raisr.cl run on the CPU.  TEST INFRASTRUCTURE.
+
+`run()` does what ClRaisr.upsample does around the kernel (raisr.py:86-133): CL_R or CL_BGRA UNORM_INT8 images, the
+Sobel / colour / Gaussian / quantiser buffers of raisr.py:19-50,82-84,111-114, one work-item per destination pixel in
+16 x 16 groups.  The libraries only exist where /root/reference does (oracle/build_ref.py); everywhere else the
+committed outputs in tests/golden/ref_cl_*.npz stand in for them (tests/golden/make_ref_cl_golden.py).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import build_ref
+
+F32 = np.float32
+# raisr.py:19-50 (host-side constants handed to the kernel)
+CSC_RGB2YUV = np.array([0.299, 0.587, 0.114, 0, -0.14713, -0.28886, 0.436, 0, 0.615, -0.51499, -0.10001, 0, 0, 0, 0, 1], F32)
+CSC_YUV2RGB = np.array([1, 0, 1.13983, 0, 1, -0.39465, -0.58060, 0, 1, 2.03211, 0, 0, 0, 0, 0, 1], F32)
+CSC_IDENTITY = np.eye(4, dtype=F32).ravel()
+SOBEL_X = np.array([-1, 0, 1, -2, 0, 2, -1, 0, 1], F32)
+SOBEL_Y = np.array([-1, -2, -1, 0, 0, 0, 1, 2, 1], F32)
+STRENGTH_Q = np.array([0.0001, 0.001], F32)      # raisr.py:111
+COHERENCE_Q = np.array([0.25, 0.5], F32)         # raisr.py:113
+
+_libs = {}
+
+
+def available() -> bool:
+    return os.path.exists(build_ref.REF_CL) or all(
+        os.path.exists(os.path.join(build_ref.OUT, "libraisr_ref_%s_%s.so" % (k, p))) for k in ("shipped", "full") for p in ("f16", "f32"))
+
+
+def _lib(kind: str, prec: str):
+    key = (kind, prec)
+    if key not in _libs:
+        if os.path.exists(build_ref.REF_CL):
+            build_ref.build()
+        lib = ctypes.CDLL(os.path.join(build_ref.OUT, "libraisr_ref_%s_%s.so" % key))
+        vp, ci = ctypes.c_void_p, ctypes.c_int
+        lib.raisr_cl_run.restype = ci
+        lib.raisr_cl_run.argtypes = [vp, ci, ci, ci, ci, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, ci, vp]
+        _libs[key] = lib
+    return _libs[key]
+
+
+def gaussian81() -> np.ndarray:
+    """raisr.py:47-59,82-84: fspecial('gaussian', [9, 9], 2), flattened."""
+    y, x = np.ogrid[-4.0:5.0, -4.0:5.0]
+    h = np.exp(-(x * x + y * y) / (2.0 * 2 * 2))
+    h[h < np.finfo(h.dtype).eps * h.max()] = 0
+    h /= h.sum()
+    return np.ascontiguousarray(h.ravel(), dtype=F32)
+
+
+def run(src: np.ndarray, filters: np.ndarray, scale: int = 2, *, kind: str = "shipped", prec: str = "f16") -> np.ndarray:
+    """src: (h, w) u8 gray or (h, w, 4) u8 BGRA; returns the destination image the kernel writes.
+    kind: "shipped" (early return active, as the file lies) | "full" (early return compiled out).
+    prec: "f16" (half is binary16) | "f32" (half kept in binary32)."""
+    assert kind in ("shipped", "full") and prec in ("f16", "f32")
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    gray = src.ndim == 2
+    sh, sw = src.shape[:2]
+    dh, dw = sh * scale, sw * scale
+    dst = np.zeros((dh, dw) if gray else (dh, dw, 4), np.uint8)
+    flt = np.ascontiguousarray(filters, dtype=F32)
+    to_yuv, from_yuv = (CSC_IDENTITY, CSC_IDENTITY) if gray else (CSC_RGB2YUV, CSC_YUV2RGB)     # raisr.py:99-105
+    g = gaussian81()
+    rc = _lib(kind, prec).raisr_cl_run(src.ctypes.data, sw, sh, src.strides[0], 1 if gray else 4, dst.ctypes.data, dw, dh, dst.strides[0],
+                                       SOBEL_X.ctypes.data, SOBEL_Y.ctypes.data, to_yuv.ctypes.data, from_yuv.ctypes.data, g.ctypes.data,
+                                       STRENGTH_Q.ctypes.data, COHERENCE_Q.ctypes.data, int(scale), flt.ctypes.data)
+    if rc != 0:
+        raise ValueError("raisr_cl_run: destination must be a multiple of the 16 x 16 work-group (raisr.py:129)")
+    return dst

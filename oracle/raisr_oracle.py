@@ -4,11 +4,14 @@ Nothing under ``oclcomputervision_b200/`` may import this module.  Only ``tests/
 ``__graft_entry__.smoke()`` and ``bench.py`` (cpu_baseline / ``--impl reference``) use it, and only
 as the checker or the timed CPU baseline.
 
-PARITY UNPINNED: the reference (/root/reference/super_resolution/raisr.py + raisr.cl) has no tests,
-no golden vectors, no CPU path, and its shipped kernel returns right after the bilinear upscale
-(raisr.cl:219-230), so there is nothing of the reference's to pin against.  Two independent
-restatements live here and are checked against each other, against closed-form cases and against
-the committed fixtures in tests/golden/:
+PARITY PIN: the reference (/root/reference/super_resolution/raisr.py + raisr.cl) has no tests, no golden
+vectors, no CPU path, and its shipped kernel returns right after the bilinear upscale (raisr.cl:219-230).
+The pin is made here instead: oracle/build_ref.py compiles the reference's own kernel source against an
+OpenCL-C shim (oracle/_ref/, see raisr_cl_ref.py) and tests/test_ref_pin.py holds both restatements below to
+its outputs (tests/golden/ref_cl.npz) -- the shipped kernel bit for bit, the full text (``quirks="as_written"``)
+within 1 LSB except hashes that rounding decides.  The INTENDED semantics (the default) and true binary16
+arithmetic have no reference artefact to be pinned to.  Two independent restatements live here and are also
+checked against each other, against closed-form cases and against the committed fixtures in tests/golden/:
 
 * ``raisr_ref``      numpy, written from the OpenCL text stage by stage (this file)
 * ``raisr_ref_c``    plain C (oracle/raisr_oracle.c) loaded through ctypes; also the timed CPU baseline
@@ -309,6 +312,8 @@ def _load():
                                               ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int]
         lib.raisr_oracle_run_bgra_ex.restype = ctypes.c_int
         lib.raisr_oracle_run_bgra_ex.argtypes = list(lib.raisr_oracle_run_bgra.argtypes) + [vp, vp, vp, ctypes.c_int]
+        lib.raisr_oracle_run_bgra_q.restype = ctypes.c_int
+        lib.raisr_oracle_run_bgra_q.argtypes = list(lib.raisr_oracle_run_bgra_ex.argtypes) + [ctypes.c_int, ctypes.c_int]
         lib.raisr_oracle_resize_u8.restype = ctypes.c_int
         lib.raisr_oracle_resize_u8.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_int, vp,
                                                ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_int]
@@ -393,10 +398,10 @@ def resize_u8_c(src: np.ndarray, out_hw, mode: str) -> np.ndarray:
 
 def raisr_ref_bgra_c(src_bgra: np.ndarray, filters: np.ndarray, s: int = 2, *, n_angle=24, n_strength=3, n_coherence=3,
                      strength_q=DEFAULT_STRENGTH_Q, coherence_q=DEFAULT_COHERENCE_Q, nthreads: int = 0,
-                     upscaler: str = "bilinear") -> Dict[str, np.ndarray]:
+                     upscaler: str = "bilinear", quirks: str = "intended", taps: str = "fp32") -> Dict[str, np.ndarray]:
     """C restatement of the colour (BGRA) path (raisr_oracle.c: raisr_oracle_run_bgra).  upscaler="bicubic": stage 1 is
     the reference's cubic_sample (raisr.cl:63-106) on each of the four channels."""
-    assert upscaler in ("bilinear", "bicubic")
+    assert upscaler in ("bilinear", "bicubic") and quirks in ("intended", "as_written") and taps in ("fp32", "fp16")
     lib = _load()
     src = np.ascontiguousarray(src_bgra, dtype=np.uint8)
     assert src.ndim == 3 and src.shape[2] == 4
@@ -407,10 +412,11 @@ def raisr_ref_bgra_c(src_bgra: np.ndarray, filters: np.ndarray, s: int = 2, *, n
     cq = np.ascontiguousarray(coherence_q, dtype=F32)
     res = dict(hash=np.empty((dh, dw), np.int32), out_f32=np.empty((dh, dw, 4), F32), out_u8=np.empty((dh, dw, 4), np.uint8),
                angle=np.empty((dh, dw), F32), L1=np.empty((dh, dw), F32), coherence=np.empty((dh, dw), F32))
-    rc = lib.raisr_oracle_run_bgra_ex(src.ctypes.data, sw, sh, src.strides[0], s, flt.ctypes.data, n_angle, n_strength, n_coherence,
+    rc = lib.raisr_oracle_run_bgra_q(src.ctypes.data, sw, sh, src.strides[0], s, flt.ctypes.data, n_angle, n_strength, n_coherence,
                                       sq.ctypes.data, cq.ctypes.data, res["hash"].ctypes.data, res["out_f32"].ctypes.data,
                                       res["out_u8"].ctypes.data, int(nthreads), res["angle"].ctypes.data, res["L1"].ctypes.data,
-                                      res["coherence"].ctypes.data, int(upscaler == "bicubic"))
+                                     res["coherence"].ctypes.data, int(upscaler == "bicubic"), int(quirks == "as_written"),
+                                     int(taps == "fp16"))
     if rc != 0:
         raise RuntimeError("raisr_oracle_run_bgra failed (%d)" % rc)
     return res

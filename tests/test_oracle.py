@@ -1,7 +1,7 @@
 """CPU tests of the oracle (oracle/): two independent restatements, closed-form answers, fixtures.
 
-The reference has no tests or golden vectors for this path, so parity with it
-is unpinned; these tests pin the oracle itself.
+The reference has no tests or golden vectors for this path; the pin against outputs
+of its own kernel is tests/test_ref_pin.py, these tests pin the oracle by independent means.
 """
 import hashlib
 import os

@@ -1,0 +1,77 @@
+"""The CUDA path against OUTPUTS OF THE REFERENCE'S OWN KERNEL.
+
+tests/golden/ref_cl.npz (see tests/test_ref_pin.py) holds what /root/reference/super_resolution/raisr.cl writes when
+it is executed on the CPU.  Here the product (through the C-ABI) is set to the same semantics -- `quirks="as_written"`,
+fp32 taps -- and compared with those images directly:
+
+  shipped kernel (bilinear only)   bilinear_only(): identical, bit for bit
+  full kernel text, `half`=binary32  upsample(): within 1 LSB, except pixels whose as-written hash rounding decides
+                                   (tests/test_ref_pin.py: undecidable() -- the oracle is used as that classifier only,
+                                   the pixels compared are the product's and the reference's); counted and bounded
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import raisr_oracle as O
+from oclcomputervision_b200 import ClRaisr, synth
+from tests.test_ref_pin import undecidable, luma_tensor_result
+
+pytestmark = pytest.mark.gpu
+
+GRAY = ["noise_x2", "smooth_x2", "lenna_x2", "smooth_x3", "smooth_x4", "flat_x2", "step_x2"]
+BGRA = ["bgra_smooth_x2", "bgra_noise_x2"]
+
+
+@pytest.fixture(scope="module")
+def ref(golden_dir):
+    return np.load(os.path.join(golden_dir, "ref_cl.npz"))
+
+
+def make(gray_mode, s, flt):
+    r = ClRaisr(gray_mode, quirks="as_written", taps="fp32")
+    setattr(r, "filters_x%d" % s, flt)
+    return r
+
+
+@pytest.mark.parametrize("name", GRAY)
+def test_shipped_kernel_output_bit_exact(ref, name):
+    src, s = ref[name + "_src"], int(ref[name + "_scale"])
+    r = make(1, s, synth.random_filters(s, seed=int(ref[name + "_fseed"])))
+    dst = np.zeros((src.shape[0] * s, src.shape[1] * s), np.uint8)
+    r.bilinear_only(src, dst, s)
+    assert np.array_equal(dst, ref[name + "_shipped_f32"])
+    r.close()
+
+
+@pytest.mark.parametrize("name", GRAY)
+def test_full_kernel_text_gray(ref, name):
+    src, s = ref[name + "_src"], int(ref[name + "_scale"])
+    r = make(1, s, synth.random_filters(s, seed=int(ref[name + "_fseed"])))
+    dst = np.zeros((src.shape[0] * s, src.shape[1] * s), np.uint8)
+    r.upsample(src, dst, s)
+    d = np.abs(dst.astype(np.int32) - ref[name + "_full_f32"].astype(np.int32))
+    loose = undecidable(O.raisr_ref(src, None, s, quirks="as_written"), s)
+    print("%s: %d of %d pixels differ, %d by more than 1 LSB, %d on a rounding-decided hash" %
+          (name, int((d > 0).sum()), d.size, int((d > 1).sum()), int(loose.sum())))
+    assert d[~loose].max() <= 1
+    assert (d[~loose] > 0).mean() < 2e-3
+    if name != "step_x2":                                         # (step_x2 is made of horizontal edges on purpose)
+        assert (d > 1).sum() <= max(3, 1e-3 * d.size)
+    r.close()
+
+
+@pytest.mark.parametrize("name", BGRA)
+def test_full_kernel_text_colour(ref, name):
+    src, s = ref[name + "_src"], int(ref[name + "_scale"])
+    r = make(0, s, synth.random_filters(s, seed=int(ref[name + "_fseed"])))
+    dst = np.zeros((src.shape[0] * s, src.shape[1] * s, 4), np.uint8)
+    r.upsample(src, dst, s)
+    d = np.abs(dst.astype(np.int32) - ref[name + "_full_f32"].astype(np.int32)).max(-1)
+    loose = undecidable(luma_tensor_result(src, s), s)
+    print("%s: %d of %d pixels differ, %d by more than 1 LSB" % (name, int((d > 0).sum()), d.size, int((d > 1).sum())))
+    assert d[~loose].max() <= 1
+    assert (d[~loose] > 0).mean() < 5e-3
+    assert (d > 1).sum() <= max(3, 2e-3 * d.size)
+    r.close()
