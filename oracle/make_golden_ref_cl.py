@@ -1,4 +1,5 @@
-"""Generates tests/golden/ref_cl.npz: OUTPUTS OF THE REFERENCE'S OWN KERNEL (raisr.cl), run here on the CPU.
+"""Generates tests/golden/ref_cl.npz and ref_cl_interp.npz: OUTPUTS OF THE REFERENCE'S OWN KERNELS (raisr.cl,
+interpolation.cl), run here on the CPU.
 
     python oracle/make_golden_ref_cl.py          # build container only: needs /root/reference
 
@@ -8,6 +9,10 @@ seed of the filter table (oclcomputervision_b200.synth.random_filters) and four 
 
     shipped_f16 / shipped_f32   the kernel as shipped (early return: bilinear only), `half` = binary16 / binary32
     full_f16 / full_f32         the early return compiled out: the whole RAISR text runs
+
+ref_cl_interp.npz holds, for BGRA and gray sources and several destination sizes (integer and fractional ratios; a
+reduction for the two kernels that have no 20 x 20 local tile), what bilinear_simple / bilinear_lds / bicubic_simple /
+bicubic_lds write, again with `half` as binary16 and as binary32.
 
 These are the vectors that pin the oracle (tests/test_ref_pin.py) and, on the GPU box, the CUDA path directly
 (tests/test_ref_pin_gpu.py); /root/reference does not travel, the fixture does.
@@ -45,6 +50,41 @@ def sources():
     }
 
 
+def interp_cases():
+    rng = np.random.default_rng(20260102)
+    lenna = np.load(os.path.join(ROOT, "tests", "golden", "lenna_x2.npz"))["src"]
+    smooth = [synth.synthetic_frame(24, 40, seed=s, sigma=2.0) for s in (21, 22, 23)]
+    srcs = {
+        "bgra_noise": rng.integers(0, 256, (24, 40, 4), dtype=np.uint8),
+        "bgra_smooth": np.stack(smooth + [np.full((24, 40), 255, np.uint8)], -1),
+        "gray_lenna": np.ascontiguousarray(lenna[200:248, 216:280]),
+    }
+    for name, src in srcs.items():
+        h, w = src.shape[:2]
+        for dh, dw in ((2 * h, 2 * w), (64, 96), (3 * h + 8, 4 * w)):      # x2; fractional ratios; anisotropic
+            if dh >= h and dh % 16 == 0 and dw % 16 == 0:
+                for method in ("bilinear", "bilinear_lds", "bicubic", "bicubic_lds"):
+                    yield name, src, (dh, dw), method
+        for method in ("bilinear", "bicubic"):                              # odd sizes and a reduction: no work-group constraint
+            yield name, src, (h + 7, 2 * w - 3), method
+            yield name, src, (h - 5, w - 9), method
+
+
+def main_interp():
+    out = {}
+    index = []
+    for name, src, hw, method in interp_cases():
+        key = "%s_%s_%dx%d" % (name, method, hw[0], hw[1])
+        out[name + "_src"] = src
+        for prec in ("f16", "f32"):
+            out[key + "_" + prec] = R.interp(src, hw, method, prec=prec)
+        index.append(key)
+    out["index"] = np.array(index)
+    path = os.path.join(ROOT, "tests", "golden", "ref_cl_interp.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(index), "cases")
+
+
 def main():
     out = {}
     for name, (src, s) in sources().items():
@@ -63,3 +103,4 @@ def main():
 
 if __name__ == "__main__":
     main()
+    main_interp()

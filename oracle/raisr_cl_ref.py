@@ -1,9 +1,11 @@
-"""ctypes front end of oracle/_ref/libraisr_ref_*.so -- the reference's own raisr.cl run on the CPU.  TEST INFRASTRUCTURE.
+"""ctypes front end of oracle/_ref/lib*_ref_*.so -- the reference's own raisr.cl and interpolation.cl run on the CPU.
+TEST INFRASTRUCTURE.
 
 `run()` does what ClRaisr.upsample does around the kernel (raisr.py:86-133): CL_R or CL_BGRA UNORM_INT8 images, the
 Sobel / colour / Gaussian / quantiser buffers of raisr.py:19-50,82-84,111-114, one work-item per destination pixel in
-16 x 16 groups.  The libraries only exist where /root/reference does (oracle/build_ref.py); everywhere else the
-committed outputs in tests/golden/ref_cl_*.npz stand in for them (tests/golden/make_ref_cl_golden.py).
+16 x 16 groups.  `interp()` does what clUtility.bilinear / bilinear_lds / bicubic / bicubic_lds do
+(basic/interpolation.py:37-117).  The libraries only exist where /root/reference does (oracle/build_ref.py); everywhere else the
+committed outputs in tests/golden/ref_cl*.npz stand in for them (oracle/make_golden_ref_cl.py).
 """
 import ctypes
 import os
@@ -26,21 +28,23 @@ _libs = {}
 
 
 def available() -> bool:
-    return os.path.exists(build_ref.REF_CL) or all(
-        os.path.exists(os.path.join(build_ref.OUT, "libraisr_ref_%s_%s.so" % (k, p))) for k in ("shipped", "full") for p in ("f16", "f32"))
+    return os.path.exists(build_ref.REF_CL) or all(os.path.exists(p) for p in build_ref.lib_paths())
+
+
+def _open(name: str):
+    if name not in _libs:
+        if os.path.exists(build_ref.REF_CL):
+            build_ref.build()
+        _libs[name] = ctypes.CDLL(os.path.join(build_ref.OUT, name))
+    return _libs[name]
 
 
 def _lib(kind: str, prec: str):
-    key = (kind, prec)
-    if key not in _libs:
-        if os.path.exists(build_ref.REF_CL):
-            build_ref.build()
-        lib = ctypes.CDLL(os.path.join(build_ref.OUT, "libraisr_ref_%s_%s.so" % key))
-        vp, ci = ctypes.c_void_p, ctypes.c_int
-        lib.raisr_cl_run.restype = ci
-        lib.raisr_cl_run.argtypes = [vp, ci, ci, ci, ci, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, ci, vp]
-        _libs[key] = lib
-    return _libs[key]
+    lib = _open("libraisr_ref_%s_%s.so" % (kind, prec))
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    lib.raisr_cl_run.restype = ci
+    lib.raisr_cl_run.argtypes = [vp, ci, ci, ci, ci, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, ci, vp]
+    return lib
 
 
 def gaussian81() -> np.ndarray:
@@ -70,4 +74,26 @@ def run(src: np.ndarray, filters: np.ndarray, scale: int = 2, *, kind: str = "sh
                                        STRENGTH_Q.ctypes.data, COHERENCE_Q.ctypes.data, int(scale), flt.ctypes.data)
     if rc != 0:
         raise ValueError("raisr_cl_run: destination must be a multiple of the 16 x 16 work-group (raisr.py:129)")
+    return dst
+
+
+INTERP_KERNELS = {"bilinear": 0, "bilinear_lds": 1, "bicubic": 2, "bicubic_lds": 3}     # clUtility method -> kernel (interpolation.py:30-33)
+
+
+def interp(src: np.ndarray, out_hw, method: str, *, prec: str = "f16") -> np.ndarray:
+    """clUtility.<method>(src, dst) (basic/interpolation.py:37-117) with the reference's own kernels.
+    src: (h, w, 4) u8 BGRA as the reference uses, or (h, w) u8 (a CL_R image; the kernels do not care)."""
+    assert prec in ("f16", "f32")
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    gray = src.ndim == 2
+    dh, dw = out_hw
+    dst = np.zeros((dh, dw) if gray else (dh, dw, 4), np.uint8)
+    lib = _open("libinterp_ref_%s.so" % prec)
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    lib.interp_cl_run.restype = ci
+    lib.interp_cl_run.argtypes = [ci, vp, ci, ci, ci, ci, vp, ci, ci, ci]
+    rc = lib.interp_cl_run(INTERP_KERNELS[method], src.ctypes.data, src.shape[1], src.shape[0], src.strides[0], 1 if gray else 4,
+                           dst.ctypes.data, dw, dh, dst.strides[0])
+    if rc != 0:
+        raise ValueError("interp_cl_run: the LDS kernels need a destination that is a multiple of the 16 x 16 work-group")
     return dst

@@ -30,8 +30,10 @@
 #define write_only
 #define CLK_LOCAL_MEM_FENCE 1
 #define CLK_NORMALIZED_COORDS_FALSE 0
+#define CLK_NORMALIZED_COORDS_TRUE 1
 #define CLK_ADDRESS_CLAMP_TO_EDGE 2
 #define CLK_FILTER_NEAREST 0
+#define CLK_FILTER_LINEAR 0x10
 #define CLK_R 0x10B0
 #define CLK_RGBA 0x10B5
 #define CLK_BGRA 0x10B6
@@ -157,6 +159,25 @@ inline float4 read_imagef(image2d_t im, sampler_t, int2 c)
     if (im->order == CLK_R) return float4(p[x] / 255.0f, 0.0f, 0.0f, 1.0f);
     p += 4 * x;
     return float4(p[2] / 255.0f, p[1] / 255.0f, p[0] / 255.0f, p[3] / 255.0f);
+}
+// float coordinates: only what interpolation.cl:12-13 uses -- CLK_NORMALIZED_COORDS_TRUE | CLK_ADDRESS_CLAMP_TO_EDGE |
+// CLK_FILTER_LINEAR, evaluated as the OpenCL 1.2 specification writes it (section 8.2): u = s * w, i0 = floor(u - 0.5),
+// a = frac(u - 0.5), T = (1-a)(1-b) T00 + a (1-b) T10 + (1-a) b T01 + a b T11 in single precision.  (Hardware samplers
+// use fixed-point weights of unspecified width, so this variant is a specification reference, not a device's bits.)
+inline float4 read_imagef(image2d_t im, sampler_t smp, float2 c)
+{
+    float u = c.x, v = c.y;
+    if (smp & CLK_NORMALIZED_COORDS_TRUE) { u *= (float)im->w; v *= (float)im->h; }
+    if (!(smp & CLK_FILTER_LINEAR)) return read_imagef(im, smp, int2((int)std::floor(u), (int)std::floor(v)));
+    const float fu = u - 0.5f, fv = v - 0.5f;
+    const int i0 = (int)std::floor(fu), j0 = (int)std::floor(fv);
+    const float a = fu - std::floor(fu), b = fv - std::floor(fv);
+    const float4 t00 = read_imagef(im, smp, int2(i0, j0)), t10 = read_imagef(im, smp, int2(i0 + 1, j0));
+    const float4 t01 = read_imagef(im, smp, int2(i0, j0 + 1)), t11 = read_imagef(im, smp, int2(i0 + 1, j0 + 1));
+    const float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
+    auto mix = [&](float p00, float p10, float p01, float p11) { return ((w00 * p00 + w10 * p10) + w01 * p01) + w11 * p11; };
+    return float4(mix(t00.x, t10.x, t01.x, t11.x), mix(t00.y, t10.y, t01.y, t11.y), mix(t00.z, t10.z, t01.z, t11.z),
+                  mix(t00.w, t10.w, t01.w, t11.w));
 }
 inline uint8_t cl_unorm8(float v)
 {

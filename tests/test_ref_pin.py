@@ -138,8 +138,37 @@ def test_binary16_evaluation_is_statistically_close(ref, name):
     assert abs(psnr(f16, res) - psnr(f16, f32)) < 1.5            # the oracle sits where the binary32 evaluation sits
 
 
-def test_live_reference_reproduces_the_fixture(ref):
-    """Only where the reference tree or its built kernel exists (oracle/_ref): re-run two cases."""
+# ---------------------------------------------------------------- basic/interpolation.cl
+def interp_index(golden_dir):
+    z = np.load(os.path.join(golden_dir, "ref_cl_interp.npz"))
+    cases = []
+    for key in z["index"]:
+        key = str(key)
+        name, rest = key.split("_", 2)[0:2], key.split("_", 2)[2]
+        method, size = rest.rsplit("_", 1)
+        cases.append((key, "_".join(name), method, tuple(int(v) for v in size.split("x"))))
+    return z, cases
+
+
+def test_interpolation_kernels_match_the_resize_oracle(golden_dir):
+    """All four kernels of interpolation.cl, `half` = binary32: the resize oracle reproduces them bit for bit; with true
+    binary16 they are within 1 LSB.  (bilinear_simple uses the hardware linear sampler, which the shim evaluates by the
+    OpenCL specification's formula -- the same formula the oracle states, so that row pins the coordinate map only.)"""
+    z, cases = interp_index(golden_dir)
+    assert len(cases) >= 40
+    for key, name, method, hw in cases:
+        src = z[name + "_src"]
+        want = O.resize_u8_c(src, hw, method)
+        assert np.array_equal(z[key + "_f32"], want), key
+        d16 = np.abs(z[key + "_f16"].astype(np.int32) - want.astype(np.int32))
+        assert d16.max() <= 1 and (d16 > 0).mean() < 0.15, key
+        if method == "bicubic_lds":      # the LDS variant computes the same function as bicubic_simple (interpolation.cl:132-211)
+            assert np.array_equal(z[key + "_f32"], z[key.replace("bicubic_lds", "bicubic") + "_f32"])
+
+
+def test_live_reference_reproduces_the_fixture(ref, golden_dir):
+    """Only where the reference tree or its built kernels exist (oracle/_ref): re-run two RAISR cases and every fifth
+    interpolation case."""
     from oracle import raisr_cl_ref as R
     if not R.available():
         pytest.skip("neither /root/reference nor oracle/_ref is present on this machine; the committed fixture stands in")
@@ -148,6 +177,10 @@ def test_live_reference_reproduces_the_fixture(ref):
         for kind in ("shipped", "full"):
             for prec in ("f16", "f32"):
                 assert np.array_equal(R.run(src, flt, s, kind=kind, prec=prec), ref["%s_%s_%s" % (name, kind, prec)])
+    z, cases = interp_index(golden_dir)
+    for key, name, method, hw in cases[::5]:
+        for prec in ("f16", "f32"):
+            assert np.array_equal(R.interp(z[name + "_src"], hw, method, prec=prec), z[key + "_" + prec]), key
 
 
 def test_reference_constants_match_the_oracle():

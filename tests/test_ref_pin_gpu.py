@@ -16,7 +16,7 @@ import pytest
 
 from oracle import raisr_oracle as O
 from oclcomputervision_b200 import ClRaisr, synth
-from tests.test_ref_pin import undecidable, luma_tensor_result
+from tests.test_ref_pin import undecidable, luma_tensor_result, interp_index
 
 pytestmark = pytest.mark.gpu
 
@@ -75,3 +75,18 @@ def test_full_kernel_text_colour(ref, name):
     assert (d[~loose] > 0).mean() < 5e-3
     assert (d > 1).sum() <= max(3, 2e-3 * d.size)
     r.close()
+
+
+def test_interpolation_kernels_bit_exact(golden_dir):
+    """clUtility.bilinear / bilinear_lds / bicubic / bicubic_lds against what the reference's interpolation.cl writes
+    (`half` = binary32): identical, BGRA and gray, integer and fractional ratios, reductions."""
+    from oclcomputervision_b200.interpolation import clUtility
+    z, cases = interp_index(golden_dir)
+    u = clUtility()
+    for key, name, method, hw in cases:
+        src = z[name + "_src"]
+        dst = np.zeros(hw if src.ndim == 2 else hw + (4,), np.uint8)
+        getattr(u, method)(src, dst)
+        assert np.array_equal(dst, z[key + "_f32"]), key
+    print("%d interpolation cases identical to the reference kernels' output" % len(cases))
+    u.close()
