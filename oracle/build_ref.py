@@ -4,7 +4,8 @@
     python oracle/build_ref.py            # needs /root/reference (this container); the GPU box uses committed fixtures
 
 The reference's device code is OpenCL C -- /root/reference/super_resolution/raisr.cl (the hot path) and
-/root/reference/basic/interpolation.cl (the stand-alone resizers); there is no OpenCL platform here
+/root/reference/basic/interpolation.cl (the stand-alone resizers), /root/reference/histeq/hist.cl
+(histogram equalisation, N4); there is no OpenCL platform here
 (SURVEY.md F5).  This recipe reads those files WHERE THEY LIE, applies the spelling changes C++ needs -- each a fixed
 regular expression, listed below and checked to have fired -- and compiles the result against
 oracle/ref_shim/cl_shim.hpp (OpenCL C types, built-ins, images, one host thread per work-item of a work-group with a
@@ -15,6 +16,7 @@ real barrier) into shared objects:
     oracle/_ref/libraisr_ref_{shipped,full}_f32.so   the same two with `half` kept in binary32 (the shim's
                                               CL_SHIM_HALF_IS_FLOAT): the kernel text in the arithmetic the oracle restates
     oracle/_ref/libinterp_ref_{f16,f32}.so    interpolation.cl: bilinear_simple, bilinear_lds, bicubic_simple, bicubic_lds
+    oracle/_ref/libhist_ref.so                histeq/hist.cl: hist, histeq_global, histeq_local_block
 
 Nothing of the reference is copied into the repository: oracle/_ref/ is git-ignored build output.
 """
@@ -26,6 +28,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_CL = "/root/reference/super_resolution/raisr.cl"
 REF_INTERP_CL = "/root/reference/basic/interpolation.cl"
+REF_HIST_CL = "/root/reference/histeq/hist.cl"
 OUT = os.path.join(HERE, "_ref")
 SHIM = os.path.join(HERE, "ref_shim", "cl_shim.hpp")
 
@@ -34,6 +37,11 @@ COMMON = [
     (r"\((half[234]|float[24]|int2)\)\s*\(", r"\1(", 10),            # vector literals: (half4)(a, b, c, d) -> half4(a, b, c, d)
     (r"(?<![\w.])(\d+\.\d+)h\b", r"half(\1f)", 10),                   # half literals: 0.5h -> half(0.5f)
     (r"^\s*#pragma .*$", r"", 5),                                     # OPENCL EXTENSION / unroll pragmas
+]
+HIST = [
+    (r"\((uint4|int2)\)\s*\(", r"\1(", 7),                            # vector literals
+    (r"^\s*#pragma .*$", r"", 4),
+    (r"__local\s+(\w+)\s*\*", r"\1 *", 1),                           # pointer INTO local memory (hist.cl:83), not a local variable
 ]
 RAISR_ONLY = [
     (r"\.s210\b", r".s210()", 3),                                     # swizzle used by CONV3x3
@@ -60,7 +68,7 @@ static void run_groups(int dw, int dh, int lw, int lh, K kernel)
         pool.emplace_back([&, t]() {
             for (int gy = 0; gy < dh / lh; ++gy)
                 for (int gx = 0; gx < dw / lw; ++gx) {
-                    cl_self = cl_item{{gx * lw + t % lw, gy * lh + t / lw}, {t % lw, t / lw}, {gx, gy}, {lw, lh}};
+                    cl_self = cl_item{{gx * lw + t % lw, gy * lh + t / lw}, {t % lw, t / lw}, {gx, gy}, {lw, lh}, {dw, dh}, {dw / lw, dh / lh}};
                     kernel();
                     pthread_barrier_wait(&bar);      // the next work-group re-uses the __local (static) arrays
                 }
@@ -108,6 +116,33 @@ extern "C" int interp_cl_run(int kernel, const uint8_t* src, int sw, int sh, int
 }
 '''
 
+HIST_DRIVER = PREAMBLE + r'''
+// eq_opencl.py:37-89: CL_R / CL_UNSIGNED_INT8 images; `hist` runs (w / 256, h) work-items in groups of (1, 32), the two
+// equalisation kernels (w, h) in groups of (16, 16)
+extern "C" int hist_cl_run(const uint8_t* img, int w, int h, int pitch, uint32_t* hist_out)
+{
+    if (w % HIST_BINS || h % HIST_THREAD_NUM) return -1;
+    image2d s{const_cast<uint8_t*>(img), w, h, pitch, CLK_R};
+    run_groups(w / HIST_BINS, h, 1, HIST_THREAD_NUM, [&]() { hist(&s, hist_out); });
+    return 0;
+}
+extern "C" int histeq_global_cl_run(const uint8_t* img, int w, int h, int pitch, uint8_t* dst, int dst_pitch, const uint8_t* mapping)
+{
+    if (w % 16 || h % 16) return -1;
+    image2d s{const_cast<uint8_t*>(img), w, h, pitch, CLK_R}, d{dst, w, h, dst_pitch, CLK_R};
+    run_groups(w, h, 16, 16, [&]() { histeq_global(&s, &d, mapping); });
+    return 0;
+}
+extern "C" int histeq_local_block_cl_run(const uint8_t* img, int w, int h, int pitch, uint8_t* dst, int dst_pitch, const float* grid,
+                                         int bw, int bh, int nx, int ny)
+{
+    if (w % 16 || h % 16) return -1;
+    image2d s{const_cast<uint8_t*>(img), w, h, pitch, CLK_R}, d{dst, w, h, dst_pitch, CLK_R};
+    run_groups(w, h, 16, 16, [&]() { histeq_local_block(&s, &d, grid, bw, bh, nx, ny); });
+    return 0;
+}
+'''
+
 # name -> (source, rewrites, driver, [(library suffix, extra compiler flags)])
 UNITS = {
     "raisr": (REF_CL, COMMON + RAISR_ONLY, RAISR_DRIVER,
@@ -115,6 +150,8 @@ UNITS = {
                for k in ("shipped", "full") for p in ("f16", "f32")]),
     "interp": (REF_INTERP_CL, COMMON, INTERP_DRIVER,
                [("libinterp_ref_%s.so" % p, ["-DCL_SHIM_HALF_IS_FLOAT"] if p == "f32" else []) for p in ("f16", "f32")]),
+    # eq_opencl.py:26: -DHIST_BINS=256 -DHIST_THREAD_NUM=32 -DHIST_N=8 (no half arithmetic in this file)
+    "hist": (REF_HIST_CL, HIST, HIST_DRIVER, [("libhist_ref.so", ["-DHIST_BINS=256", "-DHIST_THREAD_NUM=32", "-DHIST_N=8"])]),
 }
 
 

@@ -11,6 +11,8 @@ the local-block blend: the OpenCL kernel (hist.cl:139-144) works in fp32, and un
 promotion (python-float weight x np.float32 table entry -> float32) so does the reference's Python loop
 (eq_local_block.py:66-77), so `local_block_apply` below restates both.  The weights s, t and their
 products are exact in fp32 for power-of-two block sizes, which is what makes the two agree to the bit.
+The OpenCL kernels themselves (hist.cl, run on the CPU through oracle/build_ref.py) are a second pin:
+tests/test_ref_pin.py::test_hist_kernels_match_the_histeq_oracle, also with block sizes that are not powers of two.
 """
 from __future__ import annotations
 

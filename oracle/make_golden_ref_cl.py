@@ -1,5 +1,5 @@
-"""Generates tests/golden/ref_cl.npz and ref_cl_interp.npz: OUTPUTS OF THE REFERENCE'S OWN KERNELS (raisr.cl,
-interpolation.cl), run here on the CPU.
+"""Generates tests/golden/ref_cl.npz, ref_cl_interp.npz and ref_cl_hist.npz: OUTPUTS OF THE REFERENCE'S OWN KERNELS
+(raisr.cl, interpolation.cl, hist.cl), run here on the CPU.
 
     python oracle/make_golden_ref_cl.py          # build container only: needs /root/reference
 
@@ -85,6 +85,35 @@ def main_interp():
     print("wrote", path, os.path.getsize(path), "bytes,", len(index), "cases")
 
 
+def main_hist():
+    """histeq/hist.cl: tile histograms, the global LUT pass, the block-bilinear LUT blend (power-of-two and other block sizes;
+    every image stays inside nblocks * block + block / 2, beyond which the reference indexes past its tables)."""
+    from oracle import histeq_oracle as HO
+    rng = np.random.default_rng(20260103)
+    yy, xx = np.mgrid[0:256, 0:768].astype(np.float64)
+    light = 0.2 + 0.6 * (0.5 + 0.5 * np.sin(xx / 120.0) * np.cos(yy / 70.0))
+    img = np.clip(light * 255 + rng.normal(0, 18, light.shape), 0, 255).astype(np.uint8)
+    img[:40, :300] = 9                                                   # a flat region (one bin takes a whole tile row)
+    out = {"img": img, "hist": R.hist_grid(img)}
+    mapping = HO.transfer_func(out["hist"].sum(axis=(0, 1)), 1, 0.05, 2).astype(np.uint8)
+    out["mapping"] = mapping
+    out["global"] = R.histeq_global(img, mapping)
+    cases = []
+    for k, (crop, bs) in enumerate((((256, 768), (64, 256)), ((256, 768), (256, 256)), ((128, 512), (32, 256)), ((112, 480), (48, 96)),
+                                    ((240, 720), (80, 144)))):
+        sub = np.ascontiguousarray(img[:crop[0], :crop[1]])
+        maps = HO.block_mappings(sub, 0.5, 0.05, 3, bs)
+        out["local%d_crop" % k] = np.array(crop)
+        out["local%d_block" % k] = np.array(bs)
+        out["local%d_maps" % k] = maps
+        out["local%d_out" % k] = R.histeq_local_block(sub, maps, bs)
+        cases.append(k)
+    out["n_local"] = np.int32(len(cases))
+    path = os.path.join(ROOT, "tests", "golden", "ref_cl_hist.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def main():
     out = {}
     for name, (src, s) in sources().items():
@@ -104,3 +133,4 @@ def main():
 if __name__ == "__main__":
     main()
     main_interp()
+    main_hist()

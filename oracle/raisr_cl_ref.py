@@ -97,3 +97,50 @@ def interp(src: np.ndarray, out_hw, method: str, *, prec: str = "f16") -> np.nda
     if rc != 0:
         raise ValueError("interp_cl_run: the LDS kernels need a destination that is a multiple of the 16 x 16 work-group")
     return dst
+
+
+# ---------------------------------------------------------------- histeq/hist.cl as clHistEq launches it (eq_opencl.py:37-89)
+def _hist_lib():
+    lib = _open("libhist_ref.so")
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    lib.hist_cl_run.restype = ci
+    lib.hist_cl_run.argtypes = [vp, ci, ci, ci, vp]
+    lib.histeq_global_cl_run.restype = ci
+    lib.histeq_global_cl_run.argtypes = [vp, ci, ci, ci, vp, ci, vp]
+    lib.histeq_local_block_cl_run.restype = ci
+    lib.histeq_local_block_cl_run.argtypes = [vp, ci, ci, ci, vp, ci, vp, ci, ci, ci, ci]
+    return lib
+
+
+def hist_grid(gray: np.ndarray) -> np.ndarray:
+    """clHistEq.histGrid (eq_opencl.py:37-51): (h // 32, w // 256, 256) uint32."""
+    gray = np.ascontiguousarray(gray, dtype=np.uint8)
+    h, w = gray.shape
+    out = np.zeros((h // 32, w // 256, 256), np.uint32)
+    if _hist_lib().hist_cl_run(gray.ctypes.data, w, h, gray.strides[0], out.ctypes.data) != 0:
+        raise ValueError("hist: the image must be a multiple of the 256 x 32 tile")
+    return out
+
+
+def histeq_global(gray: np.ndarray, mapping: np.ndarray) -> np.ndarray:
+    """clHistEq.histeqGlobal (eq_opencl.py:53-68)."""
+    gray = np.ascontiguousarray(gray, dtype=np.uint8)
+    mapping = np.ascontiguousarray(mapping, dtype=np.uint8)
+    h, w = gray.shape
+    out = np.zeros_like(gray)
+    if _hist_lib().histeq_global_cl_run(gray.ctypes.data, w, h, gray.strides[0], out.ctypes.data, out.strides[0], mapping.ctypes.data) != 0:
+        raise ValueError("histeq_global: the image must be a multiple of the 16 x 16 work-group")
+    return out
+
+
+def histeq_local_block(gray: np.ndarray, mappings: np.ndarray, blockshape) -> np.ndarray:
+    """clHistEq.histeqLocalBlock (eq_opencl.py:70-89): mappings (ny, nx, 256), cast to float32 as the reference does."""
+    gray = np.ascontiguousarray(gray, dtype=np.uint8)
+    grid = np.ascontiguousarray(mappings, dtype=F32)
+    h, w = gray.shape
+    out = np.zeros_like(gray)
+    rc = _hist_lib().histeq_local_block_cl_run(gray.ctypes.data, w, h, gray.strides[0], out.ctypes.data, out.strides[0], grid.ctypes.data,
+                                               int(blockshape[1]), int(blockshape[0]), grid.shape[1], grid.shape[0])
+    if rc != 0:
+        raise ValueError("histeq_local_block: the image must be a multiple of the 16 x 16 work-group")
+    return out

@@ -94,7 +94,29 @@ using std::ceil;
 using std::floor;
 using std::min;
 
+typedef unsigned char uchar;
+typedef unsigned short ushort;
+typedef unsigned int uint;
+inline float clamp(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
 struct int2 { int x, y; int2() : x(0), y(0) {} int2(int a, int b) : x(a), y(b) {} };
+struct uint4 { uint x, y, z, w; uint4() : x(0), y(0), z(0), w(0) {} uint4(uint a, uint b, uint c, uint d) : x(a), y(b), z(c), w(d) {} };
+// ushortN of hist.cl:3-38 (only N = 8 is built: HIST_BINS / HIST_THREAD_NUM = 256 / 32, eq_opencl.py:26); arithmetic wraps at 16 bits
+struct ushort8 {
+    ushort s0, s1, s2, s3, s4, s5, s6, s7;
+    ushort8(int v = 0) : s0(v), s1(v), s2(v), s3(v), s4(v), s5(v), s6(v), s7(v) {}
+    ushort8& operator+=(const ushort8& o)
+    {
+        s0 += o.s0; s1 += o.s1; s2 += o.s2; s3 += o.s3; s4 += o.s4; s5 += o.s5; s6 += o.s6; s7 += o.s7;
+        return *this;
+    }
+};
+inline ushort8 vload8(int n, const ushort* p)
+{
+    ushort8 v;
+    p += 8 * n;
+    v.s0 = p[0]; v.s1 = p[1]; v.s2 = p[2]; v.s3 = p[3]; v.s4 = p[4]; v.s5 = p[5]; v.s6 = p[6]; v.s7 = p[7];
+    return v;
+}
 struct float2 {
     float x, y;
     float2() : x(0), y(0) {}
@@ -179,6 +201,17 @@ inline float4 read_imagef(image2d_t im, sampler_t smp, float2 c)
     return float4(mix(t00.x, t10.x, t01.x, t11.x), mix(t00.y, t10.y, t01.y, t11.y), mix(t00.z, t10.z, t01.z, t11.z),
                   mix(t00.w, t10.w, t01.w, t11.w));
 }
+// CL_UNSIGNED_INT8 images (hist.cl): raw bytes in, saturated bytes out; a CL_R image returns (r, 0, 0, 1)
+inline uint4 read_imageui(image2d_t im, sampler_t, int2 c)
+{
+    const int x = std::min(std::max(c.x, 0), im->w - 1), y = std::min(std::max(c.y, 0), im->h - 1);
+    return uint4(im->data[(size_t)y * im->pitch + x], 0, 0, 1);
+}
+inline void write_imageui(image2d_t im, int2 c, uint4 v)
+{
+    if (c.x < 0 || c.y < 0 || c.x >= im->w || c.y >= im->h) return;
+    im->data[(size_t)c.y * im->pitch + c.x] = (uint8_t)std::min(v.x, 255u);
+}
 inline uint8_t cl_unorm8(float v)
 {
     if (!(v == v)) return 0;                       // NaN converts to 0
@@ -195,11 +228,13 @@ inline void write_imagef(image2d_t im, int2 c, float4 v)
 }
 
 // ---- work-item functions: one host thread per work-item of the current work-group
-struct cl_item { int gid[2], lid[2], grp[2], lsz[2]; };
+struct cl_item { int gid[2], lid[2], grp[2], lsz[2], gsz[2], ngrp[2]; };
 extern thread_local cl_item cl_self;
 extern pthread_barrier_t* cl_group_barrier;
 inline int get_global_id(int d) { return cl_self.gid[d]; }
 inline int get_local_id(int d) { return cl_self.lid[d]; }
 inline int get_group_id(int d) { return cl_self.grp[d]; }
 inline int get_local_size(int d) { return cl_self.lsz[d]; }
+inline int get_global_size(int d) { return cl_self.gsz[d]; }
+inline int get_num_groups(int d) { return cl_self.ngrp[d]; }
 inline void barrier(int) { pthread_barrier_wait(cl_group_barrier); }

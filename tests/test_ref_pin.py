@@ -166,6 +166,24 @@ def test_interpolation_kernels_match_the_resize_oracle(golden_dir):
             assert np.array_equal(z[key + "_f32"], z[key.replace("bicubic_lds", "bicubic") + "_f32"])
 
 
+# ---------------------------------------------------------------- histeq/hist.cl
+def test_hist_kernels_match_the_histeq_oracle(golden_dir):
+    """hist, histeq_global and histeq_local_block of hist.cl (run as eq_opencl.py:37-89 launches them) against
+    oracle/histeq_oracle.py: integer work and an fp32 blend evaluated left to right -- bit for bit, also for block sizes
+    that are not powers of two (where the weights are no longer exact in fp32)."""
+    from oracle import histeq_oracle as HO
+    z = np.load(os.path.join(golden_dir, "ref_cl_hist.npz"))
+    img = z["img"]
+    assert np.array_equal(z["hist"], HO.hist_grid(img))
+    assert np.array_equal(z["global"], HO.global_apply(img, z["mapping"]))
+    for k in range(int(z["n_local"])):
+        crop, bs = tuple(z["local%d_crop" % k]), tuple(int(v) for v in z["local%d_block" % k])
+        sub = np.ascontiguousarray(img[:crop[0], :crop[1]])
+        maps = HO.block_mappings(sub, 0.5, 0.05, 3, bs)
+        assert np.array_equal(maps, z["local%d_maps" % k])
+        assert np.array_equal(z["local%d_out" % k], HO.local_block_apply(sub, maps, bs)), (k, bs)
+
+
 def test_live_reference_reproduces_the_fixture(ref, golden_dir):
     """Only where the reference tree or its built kernels exist (oracle/_ref): re-run two RAISR cases and every fifth
     interpolation case."""
@@ -181,6 +199,9 @@ def test_live_reference_reproduces_the_fixture(ref, golden_dir):
     for key, name, method, hw in cases[::5]:
         for prec in ("f16", "f32"):
             assert np.array_equal(R.interp(z[name + "_src"], hw, method, prec=prec), z[key + "_" + prec]), key
+    zh = np.load(os.path.join(golden_dir, "ref_cl_hist.npz"))
+    assert np.array_equal(R.hist_grid(zh["img"]), zh["hist"])
+    assert np.array_equal(R.histeq_global(zh["img"], zh["mapping"]), zh["global"])
 
 
 def test_reference_constants_match_the_oracle():

@@ -90,3 +90,20 @@ def test_interpolation_kernels_bit_exact(golden_dir):
         assert np.array_equal(dst, z[key + "_f32"]), key
     print("%d interpolation cases identical to the reference kernels' output" % len(cases))
     u.close()
+
+
+def test_hist_kernels_bit_exact(golden_dir):
+    """clHistEq.histGrid / histeqGlobal / histeqLocalBlock against what the reference's hist.cl writes."""
+    from oclcomputervision_b200.histeq import clHistEq
+    z = np.load(os.path.join(golden_dir, "ref_cl_hist.npz"))
+    img = z["img"]
+    cl = clHistEq.getInstance()
+    hist, _ = cl.histGrid(img)
+    assert np.array_equal(hist, z["hist"])
+    out, _ = cl.histeqGlobal(img, z["mapping"])
+    assert np.array_equal(out, z["global"])
+    for k in range(int(z["n_local"])):
+        crop, bs = tuple(z["local%d_crop" % k]), tuple(int(v) for v in z["local%d_block" % k])
+        sub = np.ascontiguousarray(img[:crop[0], :crop[1]])
+        out, _ = cl.histeqLocalBlock(sub, z["local%d_maps" % k], bs)
+        assert np.array_equal(out, z["local%d_out" % k]), (k, bs)
