@@ -18,7 +18,8 @@ real barrier) into shared objects:
     oracle/_ref/libinterp_ref_{f16,f32}.so    interpolation.cl: bilinear_simple, bilinear_lds, bicubic_simple, bicubic_lds
     oracle/_ref/libhist_ref.so                histeq/hist.cl: hist, histeq_global, histeq_local_block
 
-Nothing of the reference is copied into the repository: oracle/_ref/ is git-ignored build output.
+Nothing of the reference is copied into the repository: the rewritten text is piped to the compiler, and oracle/_ref/
+(git-ignored) only ever holds the shared objects.
 """
 import os
 import re
@@ -174,15 +175,11 @@ def build(force=False):
             text, hits = re.subn(pat, rep, text, flags=re.M)
             if hits < min_hits:
                 raise RuntimeError("%s: rewrite %r fired %d times (expected >= %d): the reference source changed" % (name, pat, hits, min_hits))
-        gen = os.path.join(OUT, name + "_cl_gen.cpp")
-        with open(gen, "w") as f:
-            f.write("// GENERATED by oracle/build_ref.py from %s -- build output, not part of the repository\n" % source)
-            f.write('#include "../ref_shim/cl_shim.hpp"\n')
-            f.write(text)
-            f.write(driver)
+        # the translation unit goes to the compiler through a pipe: no reference-derived source file is ever written
+        unit = ("// generated by oracle/build_ref.py from %s\n" % source) + '#include "cl_shim.hpp"\n' + text + driver
         for (lib, flags), path in zip(libs, paths):
-            subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-w"]
-                                  + flags + ["-o", path, gen])
+            subprocess.run([cxx, "-x", "c++", "-", "-I", os.path.dirname(SHIM), "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread",
+                            "-ffp-contract=off", "-fno-fast-math", "-w"] + flags + ["-o", path], input=unit.encode(), check=True)
     return lib_paths()
 
 
