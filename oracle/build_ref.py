@@ -15,6 +15,7 @@ real barrier) into shared objects:
     oracle/_ref/libraisr_ref_full_f16.so      the same text with that one `#if 1` switched off: the "dead" RAISR code runs
     oracle/_ref/libraisr_ref_{shipped,full}_f32.so   the same two with `half` kept in binary32 (the shim's
                                               CL_SHIM_HALF_IS_FLOAT): the kernel text in the arithmetic the oracle restates
+    oracle/_ref/libraisr_ref_intended_{f16,f32}.so   the full text with the three slips of raisr.cl:271,310,316 corrected (INTENDED_FIXES)
     oracle/_ref/libinterp_ref_{f16,f32}.so    interpolation.cl: bilinear_simple, bilinear_lds, bicubic_simple, bicubic_lds
     oracle/_ref/libhist_ref.so                histeq/hist.cl: hist, histeq_global, histeq_local_block
 
@@ -48,6 +49,15 @@ RAISR_ONLY = [
     (r"\.s210\b", r".s210()", 3),                                     # swizzle used by CONV3x3
     (r"__local\s+half4\s+block\[", r"half4 block[", 2),               # __local pointer parameters of the two samplers
     (r"^#if 1\s*$", r"#if RAISR_EARLY_RETURN", 1),                    # the early return of raisr.cl:219, now a build switch
+]
+
+# The "intended" build only: the three slips of the dead code corrected IN THE REFERENCE'S TEXT, one token
+# each, so that the semantics the product defaults to are also computed by the reference's own kernel -- everything around the three
+# tokens (window geometry, Sobel flip, gaussian[j][i], the eigen formulas, NaN behaviour of sqrt(L2), the 121-tap loop) is the reference's
+INTENDED_FIXES = [
+    (r"ma \+= gx \* gy \* gaussian\[j\]\[i\];", r"ma += gx * gx * gaussian[j][i];", 1),                       # raisr.cl:271
+    (r"if \(L1 < coherence_quantizers\[i\]\)", r"if (coherence < coherence_quantizers[i])", 1),              # raisr.cl:310
+    (r"\(\(\(angle_idx \* NUM_STRENGTH\) \* NUM_COHERENCE", r"(((angle_idx * NUM_STRENGTH + strength_idx) * NUM_COHERENCE", 1),  # raisr.cl:316
 ]
 
 PREAMBLE = r'''
@@ -151,6 +161,9 @@ UNITS = {
                for k in ("shipped", "full") for p in ("f16", "f32")]),
     "interp": (REF_INTERP_CL, COMMON, INTERP_DRIVER,
                [("libinterp_ref_%s.so" % p, ["-DCL_SHIM_HALF_IS_FLOAT"] if p == "f32" else []) for p in ("f16", "f32")]),
+    "raisr_intended": (REF_CL, COMMON + RAISR_ONLY + INTENDED_FIXES, RAISR_DRIVER,
+                       [("libraisr_ref_intended_%s.so" % p, ["-DRAISR_EARLY_RETURN=0"] + (["-DCL_SHIM_HALF_IS_FLOAT"] if p == "f32" else []))
+                        for p in ("f16", "f32")]),
     # eq_opencl.py:26: -DHIST_BINS=256 -DHIST_THREAD_NUM=32 -DHIST_N=8 (no half arithmetic in this file)
     "hist": (REF_HIST_CL, HIST, HIST_DRIVER, [("libhist_ref.so", ["-DHIST_BINS=256", "-DHIST_THREAD_NUM=32", "-DHIST_N=8"])]),
 }

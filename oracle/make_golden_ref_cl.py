@@ -9,6 +9,8 @@ seed of the filter table (oclcomputervision_b200.synth.random_filters) and four 
 
     shipped_f16 / shipped_f32   the kernel as shipped (early return: bilinear only), `half` = binary16 / binary32
     full_f16 / full_f32         the early return compiled out: the whole RAISR text runs
+    intended_f16 / intended_f32 as full, with the three slips of raisr.cl:271,310,316 corrected in the text (one token each,
+                                oracle/build_ref.py: INTENDED_FIXES) -- the semantics the product defaults to
 
 ref_cl_interp.npz holds, for BGRA and gray sources and several destination sizes (integer and fractional ratios; a
 reduction for the two kernels that have no 20 x 20 local tile), what bilinear_simple / bilinear_lds / bicubic_simple /
@@ -27,7 +29,7 @@ sys.path.insert(0, ROOT)
 from oracle import raisr_cl_ref as R  # noqa: E402
 from oclcomputervision_b200 import synth  # noqa: E402
 
-VARIANTS = [(k, p) for k in ("shipped", "full") for p in ("f16", "f32")]
+VARIANTS = [(k, p) for k in ("shipped", "full", "intended") for p in ("f16", "f32")]
 
 
 def sources():

@@ -9,8 +9,9 @@ vectors, no CPU path, and its shipped kernel returns right after the bilinear up
 The pin is made here instead: oracle/build_ref.py compiles the reference's own kernel source against an
 OpenCL-C shim (oracle/_ref/, see raisr_cl_ref.py) and tests/test_ref_pin.py holds both restatements below to
 its outputs (tests/golden/ref_cl.npz) -- the shipped kernel bit for bit, the full text (``quirks="as_written"``)
-within 1 LSB except hashes that rounding decides.  The INTENDED semantics (the default) and true binary16
-arithmetic have no reference artefact to be pinned to.  Two independent restatements live here and are also
+within 1 LSB except hashes that rounding decides, and the INTENDED semantics (the default) the same way against the
+reference's text with its three slips corrected, one token each (build_ref.INTENDED_FIXES).  True binary16 arithmetic
+is compared statistically only.  Two independent restatements live here and are also
 checked against each other, against closed-form cases and against the committed fixtures in tests/golden/:
 
 * ``raisr_ref``      numpy, written from the OpenCL text stage by stage (this file)

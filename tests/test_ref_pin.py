@@ -4,7 +4,9 @@ tests/golden/ref_cl.npz holds what /root/reference/super_resolution/raisr.cl its
 when it is run on the CPU (oracle/build_ref.py compiles the file where it lies against an OpenCL-C shim;
 oracle/make_golden_ref_cl.py made the fixture).  Two evaluations of the same text are stored: `half` as binary32
 ("f32", the arithmetic SURVEY.md 8(c) tells the oracle to restate) and `half` as true binary16 ("f16", what a
-cl_khr_fp16 device computes); and two builds: as shipped (early return, raisr.cl:219-230) and with that `#if 1` off.
+cl_khr_fp16 device computes); and three builds: as shipped (early return, raisr.cl:219-230), with that `#if 1` off
+("full"), and "intended" = full with the three slips of raisr.cl:271,310,316 corrected in the reference's text, one token
+each (oracle/build_ref.py: INTENDED_FIXES) -- the semantics the product and the oracle default to.
 
 What is asserted
   shipped_f32, gray   == oracle bilinear, bit for bit
@@ -14,6 +16,7 @@ What is asserted
                       within 1e-5 of a bin edge (north_star's excuse), or the angle bin changes when L1 moves by 4 ulp.
                       The second kind is specific to the text as written: with ma = mb (raisr.cl:271) a horizontal edge
                       gives mb ~ 0 and L1 - md cancels to +-1 ulp of L1, so atan2(mb, L1 - md) is rounding noise
+  intended_f32        == oracle(quirks="intended"), same rule (bin edges of angle, strength and coherence)
   full_f16            statistical only: binary16 tensors underflow (L1 thresholds are 1e-4 / 1e-3), so hashes flip
 """
 import os
@@ -38,10 +41,11 @@ def case(ref, name):
     return ref[name + "_src"], s, synth.random_filters(s, seed=int(ref[name + "_fseed"]))
 
 
-def undecidable(res, s, n_angle=24):
-    """Pixels whose as-written hash no two correct evaluations need agree on (see the module docstring).
-    res: the numpy oracle's result (it carries the tensor planes mb, md)."""
-    loose = O.edge_distance(res, quirks="as_written") < 1e-5
+def undecidable(res, s, n_angle=24, quirks="as_written"):
+    """Pixels whose hash no two correct evaluations need agree on (see the module docstring).
+    res: the numpy oracle's result (it carries the tensor planes mb, md).  The L1 - md cancellation also exists with the
+    intended tensor: whenever |mb| << |md - ma| (a gradient close to an axis) L1 - md is below one ulp of L1."""
+    loose = O.edge_distance(res, quirks=quirks) < 1e-5
     L1, mb, md = res["L1"].astype(np.float64), res["mb"].astype(np.float64), res["md"].astype(np.float64)
     delta = 4 * np.finfo(np.float32).eps * np.abs(L1)              # rounding noise of L1 = T/2 + sqrt(..), in absolute terms
 
@@ -56,13 +60,13 @@ def undecidable(res, s, n_angle=24):
     return loose
 
 
-def luma_tensor_result(src_bgra, s):
+def luma_tensor_result(src_bgra, s, quirks="as_written"):
     """The numpy oracle's hash stage on the Y plane of a BGRA source (raisr.cl:212-215 then 236-317)."""
     ext = [O.upscale_ext(np.ascontiguousarray(src_bgra[..., c]), s) for c in range(4)]
     m = np.float32([0.299, 0.587, 0.114, 0.0])                     # raisr.py:20, first row
     y = ((m[0] * ext[2] + m[1] * ext[1]) + m[2] * ext[0]) + m[3] * ext[3]
     ma, mb, md = O.tensor(y.astype(np.float32))
-    theta, L1, coh, h = O.eigen_hash(ma, mb, md, s, quirks="as_written")
+    theta, L1, coh, h = O.eigen_hash(ma, mb, md, s, quirks=quirks)
     return dict(ma=ma, mb=mb, md=md, angle=theta, L1=L1, coherence=coh, hash=h)
 
 
@@ -122,6 +126,36 @@ def test_full_kernel_text_matches_as_written_oracle_colour(ref, name):
     assert d[~loose].max() <= 1
     assert (d[~loose] > 0).mean() < 5e-3
     assert loose.mean() < 0.02 and (d > 1).sum() <= max(3, 2e-3 * d.size)
+
+
+@pytest.mark.parametrize("name", GRAY)
+def test_corrected_kernel_text_matches_intended_oracle(ref, name):
+    """The default semantics: the reference's text with the three slips corrected vs oracle(quirks="intended")."""
+    src, s, flt = case(ref, name)
+    res = O.raisr_ref_c(src, flt, s, quirks="intended", taps="fp32")
+    internals = O.raisr_ref(src, None, s, quirks="intended")
+    assert np.array_equal(internals["hash"], res["hash"])
+    got = ref[name + "_intended_f32"]
+    d = np.abs(got.astype(np.int32) - res["out_u8"].astype(np.int32))
+    loose = undecidable(internals, s, quirks="intended")
+    assert d[~loose].max() <= 1 and (d[~loose] > 0).mean() < 2e-3
+    if name != "step_x2":
+        assert loose.mean() < 0.08 and (d > 1).sum() <= max(3, 1e-3 * d.size)
+    if name != "flat_x2":
+        assert (ref[name + "_full_f32"] != got).mean() > 0.05      # and the three tokens do change the picture
+
+
+@pytest.mark.parametrize("name", BGRA)
+def test_corrected_kernel_text_matches_intended_oracle_colour(ref, name):
+    src, s, flt = case(ref, name)
+    res = O.raisr_ref_bgra_c(src, flt, s, quirks="intended", taps="fp32")
+    internals = luma_tensor_result(src, s, quirks="intended")
+    assert (internals["hash"] != res["hash"]).mean() < 1e-3
+    got = ref[name + "_intended_f32"]
+    d = np.abs(got.astype(np.int32) - res["out_u8"].astype(np.int32)).max(-1)
+    loose = undecidable(internals, s, quirks="intended") | (internals["hash"] != res["hash"])
+    assert d[~loose].max() <= 1 and (d[~loose] > 0).mean() < 5e-3
+    assert loose.mean() < 0.08 and (d > 1).sum() <= max(3, 2e-3 * d.size)
 
 
 @pytest.mark.parametrize("name", GRAY + BGRA)
@@ -192,7 +226,7 @@ def test_live_reference_reproduces_the_fixture(ref, golden_dir):
         pytest.skip("neither /root/reference nor oracle/_ref is present on this machine; the committed fixture stands in")
     for name in ("noise_x2", "bgra_noise_x2"):
         src, s, flt = case(ref, name)
-        for kind in ("shipped", "full"):
+        for kind in ("shipped", "full", "intended"):
             for prec in ("f16", "f32"):
                 assert np.array_equal(R.run(src, flt, s, kind=kind, prec=prec), ref["%s_%s_%s" % (name, kind, prec)])
     z, cases = interp_index(golden_dir)

@@ -5,6 +5,8 @@ it is executed on the CPU.  Here the product (through the C-ABI) is set to the s
 fp32 taps -- and compared with those images directly:
 
   shipped kernel (bilinear only)   bilinear_only(): identical, bit for bit
+  corrected kernel text (the three slips of raisr.cl:271,310,316 fixed in the reference's text), `half`=binary32
+                                   the product's DEFAULT semantics: same rule
   full kernel text, `half`=binary32  upsample(): within 1 LSB, except pixels whose as-written hash rounding decides
                                    (tests/test_ref_pin.py: undecidable() -- the oracle is used as that classifier only,
                                    the pixels compared are the product's and the reference's); counted and bounded
@@ -29,8 +31,8 @@ def ref(golden_dir):
     return np.load(os.path.join(golden_dir, "ref_cl.npz"))
 
 
-def make(gray_mode, s, flt):
-    r = ClRaisr(gray_mode, quirks="as_written", taps="fp32")
+def make(gray_mode, s, flt, quirks="as_written"):
+    r = ClRaisr(gray_mode, quirks=quirks, taps="fp32")
     setattr(r, "filters_x%d" % s, flt)
     return r
 
@@ -59,6 +61,28 @@ def test_full_kernel_text_gray(ref, name):
     assert (d[~loose] > 0).mean() < 2e-3
     if name != "step_x2":                                         # (step_x2 is made of horizontal edges on purpose)
         assert (d > 1).sum() <= max(3, 1e-3 * d.size)
+    r.close()
+
+
+@pytest.mark.parametrize("name", GRAY + BGRA)
+def test_corrected_kernel_text_is_the_default_semantics(ref, name):
+    """The product's default (`quirks="intended"`) against the reference's text with its three slips corrected
+    (oracle/build_ref.py: INTENDED_FIXES), `half` = binary32."""
+    src, s = ref[name + "_src"], int(ref[name + "_scale"])
+    gray = src.ndim == 2
+    r = make(1 if gray else 0, s, synth.random_filters(s, seed=int(ref[name + "_fseed"])), quirks="intended")
+    dst = np.zeros((src.shape[0] * s, src.shape[1] * s) + src.shape[2:], np.uint8)
+    r.upsample(src, dst, s)
+    d = np.abs(dst.astype(np.int32) - ref[name + "_intended_f32"].astype(np.int32))
+    d = d if gray else d.max(-1)
+    internals = O.raisr_ref(src, None, s, quirks="intended") if gray else luma_tensor_result(src, s, quirks="intended")
+    loose = undecidable(internals, s, quirks="intended")
+    print("%s (intended): %d of %d pixels differ, %d by more than 1 LSB, %d on a rounding-decided hash" %
+          (name, int((d > 0).sum()), d.size, int((d > 1).sum()), int(loose.sum())))
+    assert d[~loose].max() <= 1
+    assert (d[~loose] > 0).mean() < (2e-3 if gray else 5e-3)
+    if name != "step_x2":
+        assert (d > 1).sum() <= max(3, 2e-3 * d.size)
     r.close()
 
 
