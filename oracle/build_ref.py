@@ -16,6 +16,7 @@ real barrier) into shared objects:
     oracle/_ref/libraisr_ref_{shipped,full}_f32.so   the same two with `half` kept in binary32 (the shim's
                                               CL_SHIM_HALF_IS_FLOAT): the kernel text in the arithmetic the oracle restates
     oracle/_ref/libraisr_ref_intended_{f16,f32}.so   the full text with the three slips of raisr.cl:271,310,316 corrected (INTENDED_FIXES)
+    oracle/_ref/libraisr_ref_cubic_intended_f32.so   the same with stage 1 switched to the file's own cubic_sample (CUBIC_SWITCH)
     oracle/_ref/libinterp_ref_{f16,f32}.so    interpolation.cl: bilinear_simple, bilinear_lds, bicubic_simple, bicubic_lds
     oracle/_ref/libhist_ref.so                histeq/hist.cl: hist, histeq_global, histeq_local_block
 
@@ -59,6 +60,9 @@ INTENDED_FIXES = [
     (r"if \(L1 < coherence_quantizers\[i\]\)", r"if (coherence < coherence_quantizers[i])", 1),              # raisr.cl:310
     (r"\(\(\(angle_idx \* NUM_STRENGTH\) \* NUM_COHERENCE", r"(((angle_idx * NUM_STRENGTH + strength_idx) * NUM_COHERENCE", 1),  # raisr.cl:316
 ]
+
+# The "cubic" build only: stage 1 calls the file's own (never called) cubic_sample instead of linear_sample (raisr.cl:63-106,210)
+CUBIC_SWITCH = [(r"= linear_sample\(preload_block", r"= cubic_sample(preload_block", 1)]
 
 PREAMBLE = r'''
 #include <thread>
@@ -164,6 +168,8 @@ UNITS = {
     "raisr_intended": (REF_CL, COMMON + RAISR_ONLY + INTENDED_FIXES, RAISR_DRIVER,
                        [("libraisr_ref_intended_%s.so" % p, ["-DRAISR_EARLY_RETURN=0"] + (["-DCL_SHIM_HALF_IS_FLOAT"] if p == "f32" else []))
                         for p in ("f16", "f32")]),
+    "raisr_cubic": (REF_CL, COMMON + RAISR_ONLY + INTENDED_FIXES + CUBIC_SWITCH, RAISR_DRIVER,
+                    [("libraisr_ref_cubic_intended_f32.so", ["-DRAISR_EARLY_RETURN=0", "-DCL_SHIM_HALF_IS_FLOAT"])]),
     # eq_opencl.py:26: -DHIST_BINS=256 -DHIST_THREAD_NUM=32 -DHIST_N=8 (no half arithmetic in this file)
     "hist": (REF_HIST_CL, HIST, HIST_DRIVER, [("libhist_ref.so", ["-DHIST_BINS=256", "-DHIST_THREAD_NUM=32", "-DHIST_N=8"])]),
 }

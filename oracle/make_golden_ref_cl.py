@@ -11,6 +11,7 @@ seed of the filter table (oclcomputervision_b200.synth.random_filters) and four 
     full_f16 / full_f32         the early return compiled out: the whole RAISR text runs
     intended_f16 / intended_f32 as full, with the three slips of raisr.cl:271,310,316 corrected in the text (one token each,
                                 oracle/build_ref.py: INTENDED_FIXES) -- the semantics the product defaults to
+    cubic_intended_f32          (five cases) as intended_f32 with stage 1 calling the file's cubic_sample (CUBIC_SWITCH)
 
 ref_cl_interp.npz holds, for BGRA and gray sources and several destination sizes (integer and fractional ratios; a
 reduction for the two kernels that have no 20 x 20 local tile), what bilinear_simple / bilinear_lds / bicubic_simple /
@@ -29,6 +30,7 @@ sys.path.insert(0, ROOT)
 from oracle import raisr_cl_ref as R  # noqa: E402
 from oclcomputervision_b200 import synth  # noqa: E402
 
+CUBIC_CASES = ("noise_x2", "smooth_x2", "lenna_x2", "smooth_x3", "bgra_noise_x2")   # + stage 1 = the file's own cubic_sample
 VARIANTS = [(k, p) for k in ("shipped", "full", "intended") for p in ("f16", "f32")]
 
 
@@ -126,6 +128,8 @@ def main():
         out[name + "_fseed"] = np.int32(fseed)
         for kind, prec in VARIANTS:
             out["%s_%s_%s" % (name, kind, prec)] = R.run(src, flt, s, kind=kind, prec=prec)
+        if name in CUBIC_CASES:
+            out[name + "_cubic_intended_f32"] = R.run(src, flt, s, kind="cubic_intended", prec="f32")
         print(name, src.shape, "x%d" % s)
     path = os.path.join(ROOT, "tests", "golden", "ref_cl.npz")
     np.savez_compressed(path, **out)

@@ -59,9 +59,10 @@ def gaussian81() -> np.ndarray:
 def run(src: np.ndarray, filters: np.ndarray, scale: int = 2, *, kind: str = "shipped", prec: str = "f16") -> np.ndarray:
     """src: (h, w) u8 gray or (h, w, 4) u8 BGRA; returns the destination image the kernel writes.
     kind: "shipped" (early return active, as the file lies) | "full" (early return compiled out) | "intended" (full, with
-    the three slips of raisr.cl:271,310,316 corrected in the text: build_ref.INTENDED_FIXES).
+    the three slips of raisr.cl:271,310,316 corrected in the text: build_ref.INTENDED_FIXES) | "cubic_intended" (the same with
+    stage 1 calling the file's cubic_sample instead of linear_sample: build_ref.CUBIC_SWITCH; prec "f32" only).
     prec: "f16" (half is binary16) | "f32" (half kept in binary32)."""
-    assert kind in ("shipped", "full", "intended") and prec in ("f16", "f32")
+    assert kind in ("shipped", "full", "intended", "cubic_intended") and prec in ("f16", "f32")
     src = np.ascontiguousarray(src, dtype=np.uint8)
     gray = src.ndim == 2
     sh, sw = src.shape[:2]

@@ -60,9 +60,10 @@ def undecidable(res, s, n_angle=24, quirks="as_written"):
     return loose
 
 
-def luma_tensor_result(src_bgra, s, quirks="as_written"):
+def luma_tensor_result(src_bgra, s, quirks="as_written", upscaler="bilinear"):
     """The numpy oracle's hash stage on the Y plane of a BGRA source (raisr.cl:212-215 then 236-317)."""
-    ext = [O.upscale_ext(np.ascontiguousarray(src_bgra[..., c]), s) for c in range(4)]
+    up = O.upscale_ext if upscaler == "bilinear" else O.upscale_ext_cubic
+    ext = [up(np.ascontiguousarray(src_bgra[..., c]), s) for c in range(4)]
     m = np.float32([0.299, 0.587, 0.114, 0.0])                     # raisr.py:20, first row
     y = ((m[0] * ext[2] + m[1] * ext[1]) + m[2] * ext[0]) + m[3] * ext[3]
     ma, mb, md = O.tensor(y.astype(np.float32))
@@ -156,6 +157,30 @@ def test_corrected_kernel_text_matches_intended_oracle_colour(ref, name):
     loose = undecidable(internals, s, quirks="intended") | (internals["hash"] != res["hash"])
     assert d[~loose].max() <= 1 and (d[~loose] > 0).mean() < 5e-3
     assert loose.mean() < 0.08 and (d > 1).sum() <= max(3, 2e-3 * d.size)
+
+
+CUBIC = ["noise_x2", "smooth_x2", "lenna_x2", "smooth_x3", "bgra_noise_x2"]
+
+
+@pytest.mark.parametrize("name", CUBIC)
+def test_cubic_sample_as_stage_one(ref, name):
+    """The file's own cubic_sample (raisr.cl:63-106, never called there) switched in for linear_sample: the oracle's
+    `upscaler="bicubic"`, which the product offers as `ClRaisr(upscaler="bicubic")`."""
+    src, s, flt = case(ref, name)
+    got = ref[name + "_cubic_intended_f32"]
+    if src.ndim == 2:
+        res = O.raisr_ref_c(src, flt, s, upscaler="bicubic")
+        internals = O.raisr_ref(src, None, s, upscaler="bicubic")
+        assert np.array_equal(internals["hash"], res["hash"])
+        d = np.abs(got.astype(np.int32) - res["out_u8"].astype(np.int32))
+    else:
+        res = O.raisr_ref_bgra_c(src, flt, s, upscaler="bicubic")
+        internals = luma_tensor_result(src, s, quirks="intended", upscaler="bicubic")
+        d = np.abs(got.astype(np.int32) - res["out_u8"].astype(np.int32)).max(-1)
+    loose = undecidable(internals, s, quirks="intended") | (internals["hash"] != res["hash"])
+    assert d[~loose].max() <= 1 and (d[~loose] > 0).mean() < 2e-3
+    assert loose.mean() < 0.08 and (d > 1).sum() <= max(3, 1e-3 * d.size)
+    assert (got != ref[name + "_intended_f32"]).mean() > 0.05
 
 
 @pytest.mark.parametrize("name", GRAY + BGRA)

@@ -18,7 +18,7 @@ import pytest
 
 from oracle import raisr_oracle as O
 from oclcomputervision_b200 import ClRaisr, synth
-from tests.test_ref_pin import undecidable, luma_tensor_result, interp_index
+from tests.test_ref_pin import undecidable, luma_tensor_result, interp_index, CUBIC
 
 pytestmark = pytest.mark.gpu
 
@@ -83,6 +83,26 @@ def test_corrected_kernel_text_is_the_default_semantics(ref, name):
     assert (d[~loose] > 0).mean() < (2e-3 if gray else 5e-3)
     if name != "step_x2":
         assert (d > 1).sum() <= max(3, 2e-3 * d.size)
+    r.close()
+
+
+@pytest.mark.parametrize("name", CUBIC)
+def test_cubic_sample_as_stage_one(ref, name):
+    """ClRaisr(upscaler="bicubic") against the reference's text with its own cubic_sample switched in for linear_sample."""
+    src, s = ref[name + "_src"], int(ref[name + "_scale"])
+    gray = src.ndim == 2
+    r = ClRaisr(1 if gray else 0, taps="fp32", upscaler="bicubic")
+    setattr(r, "filters_x%d" % s, synth.random_filters(s, seed=int(ref[name + "_fseed"])))
+    dst = np.zeros((src.shape[0] * s, src.shape[1] * s) + src.shape[2:], np.uint8)
+    r.upsample(src, dst, s)
+    d = np.abs(dst.astype(np.int32) - ref[name + "_cubic_intended_f32"].astype(np.int32))
+    d = d if gray else d.max(-1)
+    internals = (O.raisr_ref(src, None, s, upscaler="bicubic") if gray
+                 else luma_tensor_result(src, s, quirks="intended", upscaler="bicubic"))
+    loose = undecidable(internals, s, quirks="intended")
+    print("%s (cubic stage 1): %d of %d pixels differ, %d by more than 1 LSB" % (name, int((d > 0).sum()), d.size, int((d > 1).sum())))
+    assert d[~loose].max() <= 1 and (d[~loose] > 0).mean() < 5e-3
+    assert (d > 1).sum() <= max(3, 2e-3 * d.size)
     r.close()
 
 
