@@ -2,9 +2,9 @@
 
 Run in the build container (needs /root/reference/images/lenna.png, cv2):
     python oracle/make_golden.py
-The reference itself cannot produce vectors (its kernel returns after the
-bilinear stage, it has no CPU path and cannot run without an AMD OpenCL platform), so these pin the
-oracle -- and through it the CUDA path -- against regressions, not against the reference's output.
+These fixtures are the ORACLE's outputs: they pin it -- and through it the CUDA path -- against regressions.
+The fixtures made from the reference's own kernels (run on the CPU) are tests/golden/ref_cl*.npz, see
+oracle/make_golden_ref_cl.py.
 """
 import hashlib
 import os
