@@ -118,6 +118,29 @@ def main_hist():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def main_lenna():
+    """BASELINE.json configs[0] in full: the 512 x 512 luma of the reference's images/lenna.png -> 1024 x 1024.  The three
+    binary32 outputs of the reference kernel are stored as (sha256, sparse difference against the oracle's output): the test
+    rebuilds the reference image from the oracle's and checks the hash, so the megabyte images need not be committed."""
+    import hashlib
+    from oracle import raisr_oracle as O
+    src = np.load(os.path.join(ROOT, "tests", "golden", "lenna_x2.npz"))["src"]
+    flt = synth.random_filters(2, seed=102)
+    out = {"fseed": np.int32(102)}
+    base = {"shipped": O.bilinear_u8_c(src, 2), "full": O.raisr_ref_c(src, flt, 2, quirks="as_written")["out_u8"],
+            "intended": O.raisr_ref_c(src, flt, 2)["out_u8"]}
+    for kind in ("shipped", "full", "intended"):
+        got = R.run(src, flt, 2, kind=kind, prec="f32")
+        idx = np.flatnonzero(got != base[kind])
+        out[kind + "_sha256"] = np.array(hashlib.sha256(got.tobytes()).hexdigest())
+        out[kind + "_diff_idx"] = idx.astype(np.int64)
+        out[kind + "_diff_val"] = got.ravel()[idx]
+        print("lenna 512x512", kind, "differs from the oracle at", idx.size, "of", got.size, "pixels")
+    path = os.path.join(ROOT, "tests", "golden", "ref_cl_lenna.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def main():
     out = {}
     for name, (src, s) in sources().items():
@@ -140,3 +163,4 @@ if __name__ == "__main__":
     main()
     main_interp()
     main_hist()
+    main_lenna()

@@ -18,7 +18,7 @@ import pytest
 
 from oracle import raisr_oracle as O
 from oclcomputervision_b200 import ClRaisr, synth
-from tests.test_ref_pin import undecidable, luma_tensor_result, interp_index, CUBIC
+from tests.test_ref_pin import undecidable, luma_tensor_result, interp_index, CUBIC, lenna_reference
 
 pytestmark = pytest.mark.gpu
 
@@ -151,3 +151,22 @@ def test_hist_kernels_bit_exact(golden_dir):
         sub = np.ascontiguousarray(img[:crop[0], :crop[1]])
         out, _ = cl.histeqLocalBlock(sub, z["local%d_maps" % k], bs)
         assert np.array_equal(out, z["local%d_out" % k]), (k, bs)
+
+
+def test_config1_lenna_full_frame(golden_dir):
+    """BASELINE.json configs[0] (512 x 512 lenna luma -> 1024 x 1024) against the reference kernel's output for the whole frame."""
+    src, flt, _, ref_img = lenna_reference(golden_dir)
+    dst = np.zeros((1024, 1024), np.uint8)
+    r = make(1, 2, flt)
+    r.bilinear_only(src, dst, 2)
+    assert np.array_equal(dst, ref_img["shipped"])
+    for kind, quirks in (("full", "as_written"), ("intended", "intended")):
+        rr = make(1, 2, flt, quirks=quirks)
+        rr.upsample(src, dst, 2)
+        d = np.abs(dst.astype(np.int32) - ref_img[kind].astype(np.int32))
+        loose = undecidable(O.raisr_ref(src, None, 2, quirks=quirks), 2, quirks=quirks)
+        print("lenna 512x512 (%s): %d of %d pixels differ, %d by more than 1 LSB" % (kind, int((d > 0).sum()), d.size, int((d > 1).sum())))
+        assert d[~loose].max() <= 1 and (d[~loose] > 0).mean() < 5e-5
+        assert (d > 0).sum() < 2e-4 * d.size
+        rr.close()
+    r.close()
